@@ -1,0 +1,163 @@
+/*
+ * edrl_b200.h -- C-ABI of the B200-native EDRL hot path.
+ *
+ * Two parts:
+ *   Part A  multi-bandwidth Gaussian MMD           reference: code/MMD.py:3-74
+ *   Part B  Essence-Point scoring + top-k select   reference: code/fusion_net.py:133-255 (class EPRL)
+ *
+ * The reference has no FFI layer (it is pure PyTorch; the boundary there is Python
+ * name binding, code/fusion_train.py:11 and code/fusion_net.py:817-821), so these
+ * entry points are what a ctypes binding inside the reference's MMD.py /
+ * fusion_net.py would call -- see INTEGRATION.md.  Each entry point cites the
+ * reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (sm_100a, CUDA 12.9) unless it says "host";
+ *   - every matrix is dense row-major fp32; index tensors are int32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - the return value is 0 on success, non-zero on error; edrl_last_error() then
+ *     returns a thread-local human-readable message (the Python host raises it as
+ *     ValueError / RuntimeError, mirroring the torch exceptions of the reference);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef EDRL_B200_H_
+#define EDRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDRL_ABI_VERSION 1
+
+/* flags for the MMD entry points */
+#define EDRL_MMD_TF32        0   /* Gram and G.Z on tcgen05 kind::tf32, operands rounded to TF32        */
+#define EDRL_MMD_3XTF32      1   /* hi/lo split operands, 3 MMAs per logical MMA (fp32-level accuracy)    */
+
+/* slots of the `stats` vector written by edrl_mmd_forward (8 floats) */
+#define EDRL_MMD_STAT_M       0  /* signed mean discrepancy  XX + YY - XY - YX          (code/MMD.py:66-69) */
+#define EDRL_MMD_STAT_SIGMA0  1  /* smallest bandwidth sigma_0                          (code/MMD.py:31-34) */
+#define EDRL_MMD_STAT_D       2  /* d M / d sigma_0 (the undetached-bandwidth term)        */
+#define EDRL_MMD_STAT_C       3  /* D / ((n^2 - n) * mul^(num//2))                                         */
+#define EDRL_MMD_STAT_SUMR    4  /* sum_i |z_i - mean|^2                                                    */
+#define EDRL_MMD_NUM_STATS    8
+
+int         edrl_abi_version(void);
+const char *edrl_last_error(void);
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+uint64_t    edrl_launch_count(void);
+/* Bind the calling host thread to CUDA device `device` (cudaSetDevice).  The library links its own
+ * static CUDA runtime, so a host that selects devices through another runtime instance (PyTorch)
+ * calls this before the compute entry points; they all run on the calling thread's current device. */
+int         edrl_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Part A -- MK_MMD                                                        code/MMD.py:46-74
+ * ---------------------------------------------------------------------------------------- */
+
+/* Bytes of scratch the MMD calls need for this shape.  The same buffer must be passed to
+ * forward and backward of one loss evaluation (it holds the centred TF32 operands, the row
+ * norms and the block weights that backward re-uses). */
+size_t edrl_mmd_workspace_bytes(int n_s, int n_t, int d, int flags);
+
+/* gaussian_kernel + MK_MMD forward, fused: the n x n kernel matrix is never written.
+ *   X [n_s, d], Y [n_t, d]                                        code/MMD.py:16-21
+ *   loss  -> 1 float   |XX + YY - XY - YX|                        code/MMD.py:60-72
+ *   stats -> EDRL_MMD_NUM_STATS floats (see above), consumed by edrl_mmd_backward
+ * tile_rank / tile_world shard the upper-triangular tile list across the ranks of a
+ * row-block-sharded evaluation (single GPU: 0 / 1).  With tile_world > 1 the call only
+ * accumulates this rank's partial sums into `partial` (2 doubles: sum a_i a_j K_ij,
+ * sum a_i a_j L_ij Q_ij); all-reduce them and call edrl_mmd_finalize. */
+int edrl_mmd_forward(const float *X, const float *Y, int n_s, int n_t, int d,
+                     float kernel_mul, int kernel_num, int flags,
+                     int tile_rank, int tile_world,
+                     float *loss, float *stats, double *partial,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* loss / stats from all-reduced partial sums (sharded evaluation only). */
+int edrl_mmd_finalize(const double *partial, int n_s, int n_t, float kernel_mul, int kernel_num,
+                      float *loss, float *stats, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward of MK_MMD w.r.t. the rows [row_begin, row_begin + row_count) of Z = [X; Y]
+ * (what autograd does to code/MMD.py:16-72, bandwidth NOT detached, clamp mask L >= 0):
+ *   dZ[i, :] = grad_out * sign(M) * 4 * ( rowsum(G)_i z_i - (G Z)_i )
+ * Kernel tiles are recomputed from the operands kept in `workspace`; nothing n x n is stored.
+ *   grad_out : 1 float (device), the incoming gradient of the scalar loss
+ *   dZ       : [row_count, d] */
+int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num, int flags,
+                      const float *stats, const float *grad_out,
+                      int row_begin, int row_count, float *dZ,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* gaussian_kernel(source, target) materialised (code/MMD.py:3-44) -- API completeness and
+ * parity tests only; K is [n, n] with n = n_s + n_t.  Uses the same tcgen05 Gram tiles. */
+int edrl_mmd_kernel_matrix(const float *X, const float *Y, int n_s, int n_t, int d,
+                           float kernel_mul, int kernel_num, int flags, float *K,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Part B -- Essence-Point scoring and selection                code/fusion_net.py:133-255
+ * ---------------------------------------------------------------------------------------- */
+
+/* Token statistics (F.normalize(z, dim=1) hoisted with the token mean, fusion_net.py:149,224-225):
+ *   z [B,T,F] -> zbar[b,f] = sum_t z[b,t,f] / (T * max(|z[b,:,f]|_2, 1e-12)),
+ *   also colsum[b,f] = sum_t z and colnorm[b,f] = |z[b,:,f]|_2 (kept for backward). */
+int edrl_token_stats_fwd(const float *z, int B, int T, int F,
+                         float *zbar, float *colsum, float *colnorm, void *stream);
+/* dz[b,t,f] from dzbar[b,f]. */
+int edrl_token_stats_bwd(const float *z, const float *colsum, const float *colnorm, const float *dzbar,
+                         int B, int T, int F, float *dz, void *stream);
+/* eval only (fusion_net.py:163): zmean[b,t] = mean_f z[b,t,f] / max(colnorm[b,f], 1e-12). */
+int edrl_token_featmean(const float *z, const float *colnorm, int B, int T, int F, float *zmean, void *stream);
+
+/* Proxy sampling + sample-dim normalisation (fusion_net.py:143-146,150):
+ *   z_p[c,s,f] = mu[c,f] + sigma[c,f] * eps[c,s,f];  z_pn = z_p / max(|z_p[c,:,f]|_2, 1e-12)
+ *   pnorm[c,f] = |z_p[c,:,f]|_2 (kept for backward). */
+int edrl_proxy_normalize_fwd(const float *mu, const float *sigma, const float *eps, int C, int S, int F,
+                             float *z_pn, float *pnorm, void *stream);
+/* dmu[c,f], dsigma[c,f] from dz_pn[c,s,f]. */
+int edrl_proxy_normalize_bwd(const float *mu, const float *sigma, const float *eps, const float *pnorm,
+                             const float *dz_pn, int C, int S, int F, float *dmu, float *dsigma, void *stream);
+
+/* Scores (fusion_net.py:221-225): att[b, r] = sum_f zbar[b,f] * z_pn[r,f], r = c*S + s in [0, R). */
+int edrl_score_fwd(const float *zbar, const float *z_pn, int B, int R, int F, float *att, void *stream);
+/* dzbar[b,f] = sum_r datt[b,r] z_pn[r,f];  dz_pn[r,f] = sum_b datt[b,r] zbar[b,f]. */
+int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int B, int R, int F,
+                   float *dzbar, float *dz_pn, void *stream);
+
+/* Generic row-wise top-k (torch.topk(x, k, dim=1), fusion_net.py:236-238): the k largest of each
+ * row, sorted descending, ties lowest-index-first.  x is [R, W] with row stride ld (floats).
+ * vals [R,k], idx [R,k] (int32).  k > W is an error, like torch. */
+int edrl_topk_rows(const float *x, int R, int W, int ld, int k, float *vals, int32_t *idx, void *stream);
+
+/* Label-addressed select (fusion_net.py:227-238) without masked_select:
+ *   positives of row b = att[b, y_b, :]           -> pos_val/pos_idx [B,k]
+ *   negatives of row b = concat_{c != y_b} att[b,c,:] (class-major) -> neg_val/neg_idx [B,k]
+ * y is int64 [B]; labels outside {0,1} are rejected by the host (proxies_dict, fusion_net.py:101). */
+int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k,
+                         float *pos_val, int32_t *pos_idx, float *neg_val, int32_t *neg_idx, void *stream);
+
+/* proxy_loss = mean_b exp(-mean(pos_val_b) + mean(neg_val_b))  (fusion_net.py:240-243);
+ * rowexp[b] keeps the per-row exponential for backward. */
+int edrl_proxy_loss_fwd(const float *pos_val, const float *neg_val, int B, int k,
+                        float *loss, float *rowexp, void *stream);
+/* Backward of loss + top-k + split in one pass: datt [B,C,S] is zero except at the selected
+ * positions, -g e_b/(B k) for positives and +g e_b/(B k) for negatives. grad_out: 1 float (device). */
+int edrl_select_loss_bwd(const float *rowexp, const int32_t *pos_idx, const int32_t *neg_idx,
+                         const int64_t *y, const float *grad_out, int B, int C, int S, int k,
+                         float *datt, void *stream);
+
+/* North-star extension (no reference code, oracle = torch.topk o torch.gather):
+ *   out[b, j, :] = features[b, idx[b,j], :],  features [B,T,D], idx [B,k] int32, out [B,k,D]. */
+int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T, int D, int k,
+                         float *out, void *stream);
+/* dfeatures [B,T,D] = scatter of dout [B,k,D] (indices of one row are distinct), zero elsewhere. */
+int edrl_gather_rows_bwd(const float *dout, const int32_t *idx, int B, int T, int D, int k,
+                         float *dfeatures, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDRL_B200_H_ */

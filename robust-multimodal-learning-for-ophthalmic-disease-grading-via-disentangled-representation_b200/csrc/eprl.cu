@@ -1,0 +1,809 @@
+// Part B -- Essence-Point scoring and top-k selection on sm_100a
+// (reference: class EPRL, code/fusion_net.py:133-255).  These are HBM / latency bound streaming kernels:
+// coalesced (vectorised where the shape allows) loads, warp-shuffle reductions, no tensor cores.
+//
+//   K4  token_stats_{fwd,bwd}, token_featmean : F.normalize(z, dim=1) + mean over tokens, hoisted (B3/B4)
+//   K5  proxy_normalize_{fwd,bwd}             : z_p = mu + sigma eps, normalised over the sample dim (B2/B3)
+//   K6  score_{fwd,bwd}                       : att = zbar . z_pn^T  (small fp32 GEMMs, B4)
+//   K7  topk_rows / select_topk_fwd           : exact radix select + bitonic sort, label-addressed rows (B5/B6)
+//   K8  proxy_loss_fwd / select_loss_bwd      : loss and its scatter backward (B6/B7)
+//   K9  gather_rows_{fwd,bwd}                 : feature gather by index (north-star extension)
+#include <math.h>
+
+#include "../../include/edrl_b200.h"
+#include "common.cuh"
+
+namespace edrl {
+namespace eprl {
+
+constexpr float NORM_EPS = 1e-12f;   // torch.nn.functional.normalize default eps
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------------------- K4 token statistics
+// grid (ceil(F/32), B), block (32, 8): lane -> feature column, y -> token slice
+__global__ void __launch_bounds__(256)
+token_stats_fwd_kernel(const float *__restrict__ z, int T, int F, float *__restrict__ zbar,
+                       float *__restrict__ colsum, float *__restrict__ colnorm) {
+  __shared__ float s_sum[8][33], s_sq[8][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y;
+  float sum = 0.f, sq = 0.f;
+  if (f < F) {
+    const float *zp = z + (size_t)b * T * F + f;
+#pragma unroll 4
+    for (int t = threadIdx.y; t < T; t += 8) {
+      const float v = __ldg(zp + (size_t)t * F);
+      sum += v;
+      sq = fmaf(v, v, sq);
+    }
+  }
+  s_sum[threadIdx.y][threadIdx.x] = sum;
+  s_sq[threadIdx.y][threadIdx.x] = sq;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      sum += s_sum[k][threadIdx.x];
+      sq += s_sq[k][threadIdx.x];
+    }
+    const float nrm = sqrtf(sq);
+    const size_t o = (size_t)b * F + f;
+    colsum[o] = sum;
+    colnorm[o] = nrm;
+    zbar[o] = sum / ((float)T * fmaxf(nrm, NORM_EPS));
+  }
+}
+
+// dz = alpha[b,f] + beta[b,f] * z ; alpha = dzbar/(T m), beta = -dzbar S /(T m^2 nrm) [nrm > eps]
+__global__ void __launch_bounds__(256)
+token_stats_bwd_kernel(const float *__restrict__ z, const float *__restrict__ colsum,
+                       const float *__restrict__ colnorm, const float *__restrict__ dzbar, int T, int F,
+                       size_t total, float *__restrict__ dz) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = (int)(i % F);
+  const size_t bt = i / F;
+  const size_t b = bt / T;
+  const size_t o = b * F + f;
+  const float nrm = colnorm[o];
+  const float m = fmaxf(nrm, NORM_EPS);
+  const float g = dzbar[o];
+  const float alpha = g / ((float)T * m);
+  const float beta = (nrm > NORM_EPS) ? (-g * colsum[o] / ((float)T * m * m * nrm)) : 0.f;
+  dz[i] = fmaf(beta, z[i], alpha);
+}
+
+// zmean[b,t] = mean_f z[b,t,f] / max(colnorm[b,f], eps); one warp per (b,t)
+__global__ void __launch_bounds__(256)
+token_featmean_kernel(const float *__restrict__ z, const float *__restrict__ colnorm, int B, int T, int F,
+                      float *__restrict__ zmean) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * T) return;
+  const int b = w / T;
+  const float *zp = z + (size_t)w * F;
+  const float *np_ = colnorm + (size_t)b * F;
+  float acc = 0.f;
+  for (int f = lane; f < F; f += 32) acc += zp[f] / fmaxf(np_[f], NORM_EPS);
+  acc = warp_sum(acc);
+  if (lane == 0) zmean[w] = acc / (float)F;
+}
+
+// ----------------------------------------------------------------------------- K5 proxies
+// grid (ceil(F/32), C), block (32, 32): lane -> feature, y -> sample slice
+__global__ void __launch_bounds__(1024)
+proxy_normalize_fwd_kernel(const float *__restrict__ mu, const float *__restrict__ sigma,
+                           const float *__restrict__ eps, int S, int F, float *__restrict__ z_pn,
+                           float *__restrict__ pnorm) {
+  __shared__ float s_sq[32][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.y;
+  float m = 0.f, sg = 0.f, sq = 0.f;
+  if (f < F) {
+    m = mu[(size_t)c * F + f];
+    sg = sigma[(size_t)c * F + f];
+    const float *ep = eps + (size_t)c * S * F + f;
+    for (int s = threadIdx.y; s < S; s += 32) {
+      const float v = fmaf(sg, __ldg(ep + (size_t)s * F), m);
+      sq = fmaf(v, v, sq);
+    }
+  }
+  s_sq[threadIdx.y][threadIdx.x] = sq;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) tot += s_sq[k][threadIdx.x];
+  if (f < F) {
+    const float nrm = sqrtf(tot);
+    if (threadIdx.y == 0) pnorm[(size_t)c * F + f] = nrm;
+    const float inv = 1.f / fmaxf(nrm, NORM_EPS);
+    const float *ep = eps + (size_t)c * S * F + f;
+    float *op = z_pn + (size_t)c * S * F + f;
+    for (int s = threadIdx.y; s < S; s += 32) op[(size_t)s * F] = fmaf(sg, __ldg(ep + (size_t)s * F), m) * inv;
+  }
+}
+
+// five column sums over s: g, g*eps, g*z_p, z_p, z_p*eps  ->  dmu, dsigma
+__global__ void __launch_bounds__(1024)
+proxy_normalize_bwd_kernel(const float *__restrict__ mu, const float *__restrict__ sigma,
+                           const float *__restrict__ eps, const float *__restrict__ pnorm,
+                           const float *__restrict__ dz_pn, int S, int F, float *__restrict__ dmu,
+                           float *__restrict__ dsigma) {
+  __shared__ float red[5][32][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int c = blockIdx.y;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+  float m = 0.f, sg = 0.f;
+  if (f < F) {
+    m = mu[(size_t)c * F + f];
+    sg = sigma[(size_t)c * F + f];
+    const float *ep = eps + (size_t)c * S * F + f;
+    const float *gp = dz_pn + (size_t)c * S * F + f;
+    for (int s = threadIdx.y; s < S; s += 32) {
+      const float e = __ldg(ep + (size_t)s * F);
+      const float g = __ldg(gp + (size_t)s * F);
+      const float zp = fmaf(sg, e, m);
+      a0 += g;
+      a1 = fmaf(g, e, a1);
+      a2 = fmaf(g, zp, a2);
+      a3 += zp;
+      a4 = fmaf(zp, e, a4);
+    }
+  }
+  red[0][threadIdx.y][threadIdx.x] = a0;
+  red[1][threadIdx.y][threadIdx.x] = a1;
+  red[2][threadIdx.y][threadIdx.x] = a2;
+  red[3][threadIdx.y][threadIdx.x] = a3;
+  red[4][threadIdx.y][threadIdx.x] = a4;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+    float t[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      float v = 0.f;
+      for (int k = 0; k < 32; ++k) v += red[q][k][threadIdx.x];
+      t[q] = v;
+    }
+    const float nrm = pnorm[(size_t)c * F + f];
+    const float q = fmaxf(nrm, NORM_EPS);
+    const float kk = (nrm > NORM_EPS) ? (t[2] / (q * q * nrm)) : 0.f;
+    dmu[(size_t)c * F + f] = t[0] / q - t[3] * kk;
+    dsigma[(size_t)c * F + f] = t[1] / q - t[4] * kk;
+  }
+}
+
+// ----------------------------------------------------------------------------- K6 small fp32 GEMM
+// C[m,n] = sum_k A(m,k) B(k,n), arbitrary strides; 64x64 tile, 16x16 threads, 4x4 per thread
+__global__ void __launch_bounds__(256)
+sgemm_strided_kernel(const float *__restrict__ A, long long sam, long long sak, const float *__restrict__ Bm,
+                     long long sbk, long long sbn, float *__restrict__ Cm, int M, int N, int K) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int kk, mm;
+      if (sak == 1) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+    }
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int kk, nn;
+      if (sbk == 1) { kk = e & 15; nn = e >> 4; } else { nn = e & 63; kk = e >> 6; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < K) ? __ldg(Bm + gk * sbk + gn * sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) Cm[(size_t)gm * N + gn] = acc[i][j];
+    }
+  }
+}
+
+static int sgemm(const float *A, long long sam, long long sak, const float *B, long long sbk, long long sbn, float *C,
+                 int M, int N, int K, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, M, N, K);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- K7 top-k
+// Order-preserving key: larger float <=> larger uint32 (positive NaN sorts first, like torch.topk).
+__device__ __forceinline__ uint32_t f2key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Row accessors -------------------------------------------------------------
+struct PlainRows {          // x [R, W], row stride ld
+  const float *x;
+  int W, ld;
+  __device__ __forceinline__ int width(int) const { return W; }
+  __device__ __forceinline__ const float *seg(int r, int j, int &run) const {
+    run = W - j;
+    return x + (size_t)r * ld + j;
+  }
+};
+struct EssenceRows {        // virtual rows over att [B,C,S]: v < B positives (class y_b), else negatives
+  const float *att;
+  const long long *y;
+  int B, C, S;
+  __device__ __forceinline__ int width(int v) const { return (v < B) ? S : (C - 1) * S; }
+  // pointer to element j of virtual row v and the number of contiguous elements that follow it
+  __device__ __forceinline__ const float *seg(int v, int j, int &run) const {
+    const int b = (v < B) ? v : v - B;
+    const int yb = min(max((int)y[b], 0), C - 1);   // the host rejects labels outside [0, C); never read out of bounds
+    int cls, s;
+    if (v < B) {
+      cls = yb;
+      s = j;
+    } else {
+      const int q = j / S;
+      s = j - q * S;
+      cls = q + (q >= yb ? 1 : 0);
+    }
+    run = S - s;
+    return att + ((size_t)b * C + cls) * S + s;
+  }
+};
+
+// bitonic sort (descending) of KP (power of two, <= 1024) 64-bit composites in shared memory by NT threads
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *buf, int KP, int tid) {
+  for (int size = 2; size <= KP; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < KP / 2; t += NT) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = buf[lo], b = buf[hi];
+        if ((a < b) == desc) {
+          buf[lo] = b;
+          buf[hi] = a;
+        }
+      }
+      if (NT == 32) __syncwarp(); else __syncthreads();
+    }
+  }
+}
+
+// One warp per row, the whole row in registers (W <= 32 E).  Exact k-th key by bitwise search with
+// early exit, ordered tie handling (lowest index first), then a shared-memory bitonic sort of the winners.
+template <int E, class Rows>
+__global__ void __launch_bounds__(128)
+topk_warp_kernel(Rows rows, int R, int k, int KP, float *__restrict__ vals, int *__restrict__ idx) {
+  extern __shared__ unsigned long long sbuf[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + wib;
+  if (r >= R) return;
+  unsigned long long *buf = sbuf + (size_t)wib * KP;
+  const int W = rows.width(r);
+  uint32_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int j = e * 32 + lane;
+    uint32_t kv = 0u;                      // below every real key (keys of finite floats are >= 0x00800000)
+    if (j < W) {
+      int run;
+      kv = f2key(__ldg(rows.seg(r, j, run)));
+      if (kv == 0u) kv = 1u;               // keep 0 reserved for padding (only -NaN payload ~0 maps here)
+    }
+    key[e] = kv;
+  }
+  // largest T with count(key >= T) >= k
+  uint32_t T = 0u;
+  int cnt_ge = 0;
+  bool exact = false;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c += (key[e] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) {
+      T = cand;
+      cnt_ge = c;
+      if (c == k) { exact = true; break; }   // the winner set is already determined
+    }
+  }
+  if (!exact && cnt_ge == 0) cnt_ge = W;     // T == 0: every element qualifies
+  // winners: key > T all; key == T lowest indices first.  With `exact`, every key >= T wins.
+  for (int t = lane; t < KP; t += 32) buf[t] = 0ull;
+  __syncwarp();
+  int base = 0;
+  if (exact) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool win = key[e] >= T;
+      const uint32_t m = __ballot_sync(0xffffffffu, win);
+      if (win) {
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        buf[slot] = ((unsigned long long)key[e] << 32) | (uint32_t)(0xffffffffu - (uint32_t)(e * 32 + lane));
+      }
+      base += __popc(m);
+    }
+  } else {
+    int c_gt = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) c_gt += (key[e] > T) ? 1 : 0;
+    c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+    int need_eq = k - c_gt;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool gt = key[e] > T;
+      const bool eq = key[e] == T;
+      const uint32_t m_eq = __ballot_sync(0xffffffffu, eq);
+      const int rank_eq = __popc(m_eq & ((1u << lane) - 1u));
+      const bool win = gt || (eq && rank_eq < need_eq);
+      const uint32_t m = __ballot_sync(0xffffffffu, win);
+      if (win) {
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        buf[slot] = ((unsigned long long)key[e] << 32) | (uint32_t)(0xffffffffu - (uint32_t)(e * 32 + lane));
+      }
+      base += __popc(m);
+      need_eq -= min(need_eq, __popc(m_eq));
+    }
+  }
+  __syncwarp();
+  bitonic_sort_desc<32>(buf, KP, lane);
+  for (int t = lane; t < k; t += 32) {
+    const unsigned long long c = buf[t];
+    vals[(size_t)r * k + t] = key2f((uint32_t)(c >> 32));
+    idx[(size_t)r * k + t] = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffu));
+  }
+}
+
+// One 256-thread block per row, any width: three radix passes (11 + 11 + 10 bits) with shared-memory
+// histograms; pass 1 streams the row from global memory, the candidates of the winning bucket are
+// compacted to shared memory for the later passes (falls back to re-streaming if they do not fit).
+constexpr int BLK_T = 256;
+constexpr int CAND_MAX = 4096;
+template <class Rows>
+__global__ void __launch_bounds__(BLK_T)
+topk_block_kernel(Rows rows, int R, int k, int KP, float *__restrict__ vals, int *__restrict__ idx) {
+  extern __shared__ unsigned long long sbuf[];          // KP composites (output staging + sort)
+  __shared__ unsigned int hist[2048];
+  __shared__ uint32_t cand_key[CAND_MAX];
+  __shared__ int cand_idx[CAND_MAX];
+  __shared__ unsigned int s_cnt, s_out;
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_need, s_eq_taken;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int W = rows.width(r);
+
+  // ---- pass 1: top 11 bits over the whole row
+  for (int t = tid; t < 2048; t += BLK_T) hist[t] = 0u;
+  if (tid == 0) { s_cnt = 0u; s_out = 0u; s_eq_taken = 0; }
+  __syncthreads();
+  for (int j = tid; j < W; j += BLK_T) {
+    int run;
+    const uint32_t kv = f2key(__ldg(rows.seg(r, j, run)));
+    atomicAdd(&hist[kv >> 21], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int need = k, b = 2047;
+    for (; b > 0; --b) {
+      if ((int)hist[b] >= need) break;
+      need -= (int)hist[b];
+    }
+    s_prefix = (uint32_t)b << 21;
+    s_need = need;                 // how many of bucket b are still wanted
+  }
+  __syncthreads();
+  const uint32_t bucket1 = s_prefix >> 21;
+  const int need1 = s_need;
+  const bool fits = (int)hist[bucket1] <= CAND_MAX;
+  // winners above the bucket go straight to the output staging; bucket members become candidates
+  for (int j0 = 0; j0 < W; j0 += BLK_T) {
+    const int j = j0 + tid;
+    if (j < W) {
+      int run;
+      const uint32_t kv = f2key(__ldg(rows.seg(r, j, run)));
+      const uint32_t d = kv >> 21;
+      if (d > bucket1) {
+        const unsigned int slot = atomicAdd(&s_out, 1u);
+        sbuf[slot] = ((unsigned long long)kv << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
+      } else if (d == bucket1 && fits) {
+        const unsigned int slot = atomicAdd(&s_cnt, 1u);
+        cand_key[slot] = kv;
+        cand_idx[slot] = j;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- exact threshold inside the bucket: bitwise search over the low 21 bits
+  uint32_t T = s_prefix;
+  const int ncand = fits ? (int)s_cnt : 0;
+  for (int bit = 20; bit >= 0; --bit) {
+    const uint32_t cnd = T | (1u << bit);
+    if (tid == 0) s_cnt = 0u;
+    __syncthreads();
+    int c = 0;
+    if (fits) {
+      for (int t = tid; t < ncand; t += BLK_T) c += (cand_key[t] >= cnd) ? 1 : 0;
+    } else {
+      for (int j = tid; j < W; j += BLK_T) {
+        int run;
+        const uint32_t kv = f2key(__ldg(rows.seg(r, j, run)));
+        c += ((kv >> 21) == bucket1 && kv >= cnd) ? 1 : 0;
+      }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, (unsigned)c);
+    __syncthreads();
+    if ((int)s_cnt >= need1) T = cnd;
+    __syncthreads();
+  }
+  // ---- winners inside the bucket: key > T all, key == T lowest index first (ordered, single thread scan
+  //      over the few equal keys keeps it exact and simple)
+  if (tid == 0) s_cnt = 0u;
+  __syncthreads();
+  if (fits) {
+    for (int t = tid; t < ncand; t += BLK_T) {
+      if (cand_key[t] > T) {
+        const unsigned int slot = atomicAdd(&s_out, 1u);
+        sbuf[slot] = ((unsigned long long)cand_key[t] << 32) | (uint32_t)(0xffffffffu - (uint32_t)cand_idx[t]);
+      }
+    }
+  } else {
+    for (int j = tid; j < W; j += BLK_T) {
+      int run;
+      const uint32_t kv = f2key(__ldg(rows.seg(r, j, run)));
+      if ((kv >> 21) == bucket1 && kv > T) {
+        const unsigned int slot = atomicAdd(&s_out, 1u);
+        sbuf[slot] = ((unsigned long long)kv << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
+      }
+    }
+  }
+  __syncthreads();
+  // equal keys: ascending index order.  Candidates were appended in arbitrary order, so pick the smallest
+  // remaining index repeatedly (need_eq is tiny unless the row is full of duplicates).
+  {
+    const int need_eq = k - (int)s_out;
+    for (int it = 0; it < need_eq; ++it) {
+      if (tid == 0) s_need = 0x7fffffff;
+      __syncthreads();
+      const int last = s_eq_taken;        // indices <= last - 1 already taken (last = next lower bound)
+      int best = 0x7fffffff;
+      if (fits) {
+        for (int t = tid; t < ncand; t += BLK_T)
+          if (cand_key[t] == T && cand_idx[t] >= last) best = min(best, cand_idx[t]);
+      } else {
+        for (int j = tid; j < W; j += BLK_T) {
+          int run;
+          const uint32_t kv = f2key(__ldg(rows.seg(r, j, run)));
+          if (kv == T && j >= last) best = min(best, j);
+        }
+      }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if ((tid & 31) == 0) atomicMin(&s_need, best);
+      __syncthreads();
+      if (tid == 0) {
+        const int j = s_need;
+        sbuf[s_out] = ((unsigned long long)T << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
+        s_out = s_out + 1;
+        s_eq_taken = j + 1;
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = k + tid; t < KP; t += BLK_T) sbuf[t] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc<BLK_T>(sbuf, KP, tid);
+  for (int t = tid; t < k; t += BLK_T) {
+    const unsigned long long c = sbuf[t];
+    vals[(size_t)r * k + t] = key2f((uint32_t)(c >> 32));
+    idx[(size_t)r * k + t] = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffu));
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <class Rows>
+static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, int *idx, cudaStream_t st) {
+  const int KP = next_pow2(k < 32 ? 32 : k);
+  EDRL_CHECK_ARG(KP <= 1024, "topk: k = %d is larger than the supported 1024", k);
+  if (Wmax <= 2048 && KP <= 256) {
+    const size_t smem = (size_t)4 * KP * sizeof(unsigned long long);
+    const int grid = (R + 3) / 4;
+    if (Wmax <= 256)
+      topk_warp_kernel<8, Rows><<<grid, 128, smem, st>>>(rows, R, k, KP, vals, idx);
+    else if (Wmax <= 512)
+      topk_warp_kernel<16, Rows><<<grid, 128, smem, st>>>(rows, R, k, KP, vals, idx);
+    else if (Wmax <= 1024)
+      topk_warp_kernel<32, Rows><<<grid, 128, smem, st>>>(rows, R, k, KP, vals, idx);
+    else
+      topk_warp_kernel<64, Rows><<<grid, 128, smem, st>>>(rows, R, k, KP, vals, idx);
+  } else {
+    const size_t smem = (size_t)KP * sizeof(unsigned long long);
+    topk_block_kernel<Rows><<<R, BLK_T, smem, st>>>(rows, R, k, KP, vals, idx);
+  }
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- K8 loss + scatter backward
+__global__ void __launch_bounds__(256)
+proxy_loss_fwd_kernel(const float *__restrict__ pos_val, const float *__restrict__ neg_val, int B, int k,
+                      float *__restrict__ loss, float *__restrict__ rowexp) {
+  __shared__ float s_part[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float part = 0.f;
+  for (int b = warp; b < B; b += 8) {
+    float sp = 0.f, sn = 0.f;
+    for (int j = lane; j < k; j += 32) {
+      sp += pos_val[(size_t)b * k + j];
+      sn += neg_val[(size_t)b * k + j];
+    }
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+    const float e = expf((sn - sp) / (float)k);
+    if (lane == 0) rowexp[b] = e;
+    part += e;
+  }
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    loss[0] = t / (float)B;
+  }
+}
+
+// one block per batch row: zero datt[b, :, :] then scatter the two coefficient sets
+__global__ void __launch_bounds__(256)
+select_loss_bwd_kernel(const float *__restrict__ rowexp, const int *__restrict__ pos_idx,
+                       const int *__restrict__ neg_idx, const long long *__restrict__ y,
+                       const float *__restrict__ grad_out, int B, int C, int S, int k, float *__restrict__ datt) {
+  const int b = blockIdx.x;
+  float *row = datt + (size_t)b * C * S;
+  for (int i = threadIdx.x; i < C * S; i += blockDim.x) row[i] = 0.f;
+  __syncthreads();
+  const int yb = min(max((int)y[b], 0), C - 1);
+  const float coef = grad_out[0] * rowexp[b] / ((float)B * (float)k);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    row[(size_t)yb * S + pos_idx[(size_t)b * k + j]] = -coef;
+    const int q = neg_idx[(size_t)b * k + j];
+    const int cq = q / S, s = q - cq * S;
+    const int cls = cq + (cq >= yb ? 1 : 0);
+    row[(size_t)cls * S + s] = coef;
+  }
+}
+
+// ----------------------------------------------------------------------------- K9 gather
+// one warp per gathered row; 128-bit accesses when D % 4 == 0 and pointers are 16-byte aligned
+__global__ void __launch_bounds__(256)
+gather_rows_fwd_kernel(const float *__restrict__ feat, const int *__restrict__ idx, int B, int T, int D, int k,
+                       int vec_ok, float *__restrict__ out) {
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)B * k) return;
+  const int b = (int)(w / k);
+  const int t = idx[w];
+  const float *src = feat + ((size_t)b * T + t) * D;
+  float *dst = out + (size_t)w * D;
+  if (vec_ok) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    const int n4 = D >> 2;
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {           // 4 independent 16-byte loads in flight per lane
+      const float4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + 32), v2 = __ldg(s4 + i + 64), v3 = __ldg(s4 + i + 96);
+      d4[i] = v0; d4[i + 32] = v1; d4[i + 64] = v2; d4[i + 96] = v3;
+    }
+    for (; i < n4; i += 32) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = lane; i < D; i += 32) dst[i] = __ldg(src + i);
+  }
+}
+
+// one block per batch element: inverse map in shared memory, every output row written exactly once
+__global__ void __launch_bounds__(256)
+gather_rows_bwd_kernel(const float *__restrict__ dout, const int *__restrict__ idx, int T, int D, int k, int vec_ok,
+                       float *__restrict__ dfeat) {
+  extern __shared__ int inv[];
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) inv[t] = -1;
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) inv[idx[(size_t)b * k + j]] = j;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += 8) {
+    const int j = inv[t];
+    float *dst = dfeat + ((size_t)b * T + t) * D;
+    const float *src = (j >= 0) ? dout + ((size_t)b * k + j) * D : nullptr;
+    if (vec_ok) {
+      float4 *d4 = reinterpret_cast<float4 *>(dst);
+      const float4 *s4 = reinterpret_cast<const float4 *>(src);
+      for (int i = lane; i < (D >> 2); i += 32) d4[i] = src ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int i = lane; i < D; i += 32) dst[i] = src ? __ldg(src + i) : 0.f;
+    }
+  }
+}
+
+}  // namespace eprl
+}  // namespace edrl
+
+using namespace edrl;
+using namespace edrl::eprl;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int edrl_token_stats_fwd(const float *z, int B, int T, int F, float *zbar, float *colsum, float *colnorm,
+                         void *stream) {
+  EDRL_CHECK_ARG(z && zbar && colsum && colnorm, "token_stats_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0 && B <= 65535, "token_stats_fwd: bad shape B=%d T=%d F=%d", B, T, F);
+  dim3 grid((F + 31) / 32, B), block(32, 8);
+  token_stats_fwd_kernel<<<grid, block, 0, ST(stream)>>>(z, T, F, zbar, colsum, colnorm);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_token_stats_bwd(const float *z, const float *colsum, const float *colnorm, const float *dzbar, int B, int T,
+                         int F, float *dz, void *stream) {
+  EDRL_CHECK_ARG(z && colsum && colnorm && dzbar && dz, "token_stats_bwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0, "token_stats_bwd: bad shape");
+  const size_t total = (size_t)B * T * F;
+  token_stats_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(z, colsum, colnorm, dzbar, T, F,
+                                                                                  total, dz);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_token_featmean(const float *z, const float *colnorm, int B, int T, int F, float *zmean, void *stream) {
+  EDRL_CHECK_ARG(z && colnorm && zmean, "token_featmean: null argument");
+  EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0, "token_featmean: bad shape");
+  token_featmean_kernel<<<(B * T + 7) / 8, 256, 0, ST(stream)>>>(z, colnorm, B, T, F, zmean);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_proxy_normalize_fwd(const float *mu, const float *sigma, const float *eps, int C, int S, int F, float *z_pn,
+                             float *pnorm, void *stream) {
+  EDRL_CHECK_ARG(mu && sigma && eps && z_pn && pnorm, "proxy_normalize_fwd: null argument");
+  EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_fwd: bad shape");
+  dim3 grid((F + 31) / 32, C), block(32, 32);
+  proxy_normalize_fwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, S, F, z_pn, pnorm);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_proxy_normalize_bwd(const float *mu, const float *sigma, const float *eps, const float *pnorm,
+                             const float *dz_pn, int C, int S, int F, float *dmu, float *dsigma, void *stream) {
+  EDRL_CHECK_ARG(mu && sigma && eps && pnorm && dz_pn && dmu && dsigma, "proxy_normalize_bwd: null argument");
+  EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_bwd: bad shape");
+  dim3 grid((F + 31) / 32, C), block(32, 32);
+  proxy_normalize_bwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, pnorm, dz_pn, S, F, dmu, dsigma);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_score_fwd(const float *zbar, const float *z_pn, int B, int R, int F, float *att, void *stream) {
+  EDRL_CHECK_ARG(zbar && z_pn && att, "score_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_fwd: bad shape");
+  // att[b, r] = sum_f zbar[b, f] z_pn[r, f]
+  return sgemm(zbar, F, 1, z_pn, 1, F, att, B, R, F, ST(stream));
+}
+
+int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int B, int R, int F, float *dzbar,
+                   float *dz_pn, void *stream) {
+  EDRL_CHECK_ARG(datt && zbar && z_pn, "score_bwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_bwd: bad shape");
+  if (dzbar) {   // dzbar[b, f] = sum_r datt[b, r] z_pn[r, f]
+    if (int rc = sgemm(datt, R, 1, z_pn, F, 1, dzbar, B, F, R, ST(stream))) return rc;
+  }
+  if (dz_pn) {   // dz_pn[r, f] = sum_b datt[b, r] zbar[b, f]
+    if (int rc = sgemm(datt, 1, R, zbar, F, 1, dz_pn, R, F, B, ST(stream))) return rc;
+  }
+  return 0;
+}
+
+int edrl_topk_rows(const float *x, int R, int W, int ld, int k, float *vals, int32_t *idx, void *stream) {
+  EDRL_CHECK_ARG(x && vals && idx, "topk: null argument");
+  EDRL_CHECK_ARG(R > 0 && W > 0 && ld >= W, "topk: bad shape R=%d W=%d ld=%d", R, W, ld);
+  EDRL_CHECK_ARG(k >= 1 && k <= W, "selected index k out of range (k=%d, row width %d)", k, W);
+  PlainRows rows{x, W, ld};
+  return launch_topk(rows, R, W, k, vals, idx, ST(stream));
+}
+
+int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k, float *pos_val,
+                         int32_t *pos_idx, float *neg_val, int32_t *neg_idx, void *stream) {
+  EDRL_CHECK_ARG(att && y && pos_val && pos_idx && neg_val && neg_idx, "select_topk_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && C >= 2 && S > 0, "select_topk_fwd: bad shape B=%d C=%d S=%d", B, C, S);
+  EDRL_CHECK_ARG(k >= 1 && k <= S, "selected index k out of range (k=%d, row width %d)", k, S);
+  EDRL_CHECK_ARG(pos_val + (size_t)B * k == neg_val && pos_idx + (size_t)B * k == neg_idx,
+                 "select_topk_fwd: pos/neg outputs must be the two halves of one [2B, k] buffer");
+  EssenceRows rows{att, reinterpret_cast<const long long *>(y), B, C, S};
+  return launch_topk(rows, 2 * B, (C - 1) * S, k, pos_val, pos_idx, ST(stream));
+}
+
+int edrl_proxy_loss_fwd(const float *pos_val, const float *neg_val, int B, int k, float *loss, float *rowexp,
+                        void *stream) {
+  EDRL_CHECK_ARG(pos_val && neg_val && loss && rowexp, "proxy_loss_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && k > 0, "proxy_loss_fwd: bad shape");
+  proxy_loss_fwd_kernel<<<1, 256, 0, ST(stream)>>>(pos_val, neg_val, B, k, loss, rowexp);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_select_loss_bwd(const float *rowexp, const int32_t *pos_idx, const int32_t *neg_idx, const int64_t *y,
+                         const float *grad_out, int B, int C, int S, int k, float *datt, void *stream) {
+  EDRL_CHECK_ARG(rowexp && pos_idx && neg_idx && y && grad_out && datt, "select_loss_bwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && C >= 2 && S > 0 && k > 0, "select_loss_bwd: bad shape");
+  select_loss_bwd_kernel<<<B, 256, 0, ST(stream)>>>(rowexp, pos_idx, neg_idx,
+                                                    reinterpret_cast<const long long *>(y), grad_out, B, C, S, k, datt);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+static int vec4_ok(const void *a, const void *b, int D) {
+  return (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
+int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T, int D, int k, float *out,
+                         void *stream) {
+  EDRL_CHECK_ARG(features && idx && out, "gather_rows_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && T > 0 && D > 0 && k > 0, "gather_rows_fwd: bad shape");
+  const long long rows = (long long)B * k;
+  gather_rows_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(features, idx, B, T, D, k,
+                                                                             vec4_ok(features, out, D), out);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_gather_rows_bwd(const float *dout, const int32_t *idx, int B, int T, int D, int k, float *dfeatures,
+                         void *stream) {
+  EDRL_CHECK_ARG(dout && idx && dfeatures, "gather_rows_bwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && T > 0 && D > 0 && k > 0, "gather_rows_bwd: bad shape");
+  EDRL_CHECK_ARG((size_t)T * sizeof(int) <= 48 * 1024, "gather_rows_bwd: T = %d too large", T);
+  gather_rows_bwd_kernel<<<B, 256, (size_t)T * sizeof(int), ST(stream)>>>(dout, idx, T, D, k,
+                                                                          vec4_ok(dout, dfeatures, D), dfeatures);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1090 @@
+// Part A -- multi-bandwidth Gaussian MMD on sm_100a (reference: code/MMD.py:3-74).
+//
+//   K1  prep_colsum / prep_center : Z = [X; Y] centred, rounded to TF32 (hi [+ lo]), transposed copy,
+//                                   row norms r_i, block weights a_i, sum r  -> analytic bandwidth
+//   K2  mmd_fwd_kernel            : persistent, warp-specialised: TMA -> smem ring -> tcgen05.mma (kind::tf32)
+//                                   -> TMEM (2 accumulator stages) -> fused distance / exp-sum / block-reduce
+//                                   epilogue.  Only upper-triangular 128x128 tiles are computed; the n x n
+//                                   kernel matrix never leaves the SM.
+//   K3  mmd_bwd_kernel            : one CTA per (128-row panel, 256-column slice of d).  Re-computes the Gram
+//                                   tiles, forms G in shared memory as a TF32 A-operand and accumulates
+//                                   G.Z_J in TMEM with a second tcgen05.mma; nothing n x n is stored.
+//
+// Math: L_ij = max(0, r_i + r_j - 2 z_i.z_j); sigma_k = sigma_0 mul^k;
+//   M = sum_ij a_i a_j sum_k exp(-L_ij / sigma_k),  a_i = 1/n_s (source rows) or -1/n_t (target rows);
+//   Q_ij = sum_k exp(-L_ij / sigma_k) / mul^k;  D = sum_ij a_i a_j L_ij Q_ij / sigma_0^2;
+//   G_ij = (-a_i a_j Q_ij / sigma_0 + c) [L_raw >= 0],  c = D / ((n^2 - n) mul^(num/2));
+//   dZ_i = g sign(M) 4 (rowsum(G)_i z_i - (G Z)_i).
+// Centring Z (distances are translation invariant) keeps TF32 rounding relative to the spread of the data
+// and makes sum(L) = 2 n sum_i |z_i|^2 exactly the reference's bandwidth statistic (code/MMD.py:31).
+#include <math.h>
+
+#include "../../include/edrl_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace edrl {
+namespace mmd {
+
+using namespace ptx;
+
+constexpr int BM = 128;          // tile rows (I)
+constexpr int BN = 128;          // tile cols (J)
+constexpr int BK = 32;           // K chunk in floats = one 128-byte swizzle atom
+constexpr int UMMA_K = 8;        // tf32: 32 bytes per MMA K step
+constexpr int TILE_BYTES = BM * BK * 4;   // 16 KiB: one operand chunk
+constexpr int MAX_KERNELS = 16;  // generic (non mul==2) path: at most this many bandwidths
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ----------------------------------------------------------------------------- workspace
+struct Layout {
+  int n, n_pad, d_pad;
+  bool split3;
+  size_t off_acc, off_colsum, off_r, off_a, off_zhi, off_zthi, off_zlo, off_ztlo, total;
+  size_t zero_bytes;  // [off_acc, off_acc + zero_bytes) must be cleared before prep
+};
+
+static Layout make_layout(int n_s, int n_t, int d, int flags) {
+  Layout L;
+  L.n = n_s + n_t;
+  L.n_pad = (int)align_up((size_t)L.n, 128);
+  L.d_pad = (int)align_up((size_t)d, 32);
+  L.split3 = (flags & EDRL_MMD_3XTF32) != 0;
+  size_t o = 0;
+  L.off_acc = o;      o += 256;                                   // 8 doubles + ticket counter
+  L.off_colsum = o;   o += align_up((size_t)L.d_pad * 8, 256);    // double[d_pad]
+  L.off_r = o;        o += align_up((size_t)L.n_pad * 8, 256);    // double[n_pad]
+  L.zero_bytes = o - L.off_acc;
+  L.off_a = o;        o += align_up((size_t)L.n_pad * 4, 256);    // float[n_pad]
+  o = align_up(o, 1024);
+  size_t zbytes = align_up((size_t)L.n_pad * L.d_pad * 4, 1024);
+  L.off_zhi = o;      o += zbytes;
+  L.off_zthi = o;     o += zbytes;
+  L.off_zlo = o;      if (L.split3) o += zbytes;
+  L.off_ztlo = o;     if (L.split3) o += zbytes;
+  L.total = o;
+  return L;
+}
+
+// ----------------------------------------------------------------------------- K1: prep
+// column sums of Z = [X; Y] in double (for the mean)
+__global__ void __launch_bounds__(128) prep_colsum_kernel(const float *__restrict__ X, const float *__restrict__ Y,
+                                                          int n_s, int n, int d, double *__restrict__ colsum) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * 64;
+  if (col >= d) return;
+  float acc = 0.f;
+  const int r1 = min(r0 + 64, n);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const float *src = (r < n_s) ? (X + (size_t)r * d) : (Y + (size_t)(r - n_s) * d);
+    acc += __ldg(src + col);
+  }
+  atomicAdd(colsum + col, (double)acc);
+}
+
+// centre, round to tf32 (hi, optionally lo), write Z [n_pad, d_pad] and Z^T [d_pad, n_pad], row norms, weights
+template <bool SPLIT3>
+__global__ void __launch_bounds__(256)
+prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int n_s, int n_t, int d, int n_pad,
+                   int d_pad, const double *__restrict__ colsum, float *__restrict__ zhi, float *__restrict__ zthi,
+                   float *__restrict__ zlo, float *__restrict__ ztlo, double *__restrict__ racc,
+                   float *__restrict__ a, double *__restrict__ acc) {
+  __shared__ float tile_hi[32][33];
+  __shared__ float tile_lo[SPLIT3 ? 32 : 1][33];
+  __shared__ float blk_sum[8];
+  const int n = n_s + n_t;
+  const int lane = threadIdx.x, wy = threadIdx.y;
+  const int row0 = blockIdx.x * 32;
+  const double inv_n = 1.0 / (double)n;
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ct = blockIdx.y; ct < d_pad / 32; ct += gridDim.y) {
+    const int col = ct * 32 + lane;
+    const float mean = (col < d) ? (float)(colsum[col] * inv_n) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int rr = wy * 4 + k;
+      const int row = row0 + rr;
+      float v = 0.f;
+      if (row < n && col < d) {
+        const float *src = (row < n_s) ? (X + (size_t)row * d) : (Y + (size_t)(row - n_s) * d);
+        v = __ldg(src + col) - mean;
+      }
+      const float hi = to_tf32(v);
+      zhi[(size_t)row * d_pad + col] = hi;
+      tile_hi[rr][lane] = hi;
+      if (SPLIT3) {
+        const float lo = to_tf32(v - hi);
+        zlo[(size_t)row * d_pad + col] = lo;
+        tile_lo[rr][lane] = lo;
+        rs[k] = fmaf(v, v, rs[k]);
+      } else {
+        rs[k] = fmaf(hi, hi, rs[k]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int cc = wy * 4 + k;
+      zthi[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_hi[lane][cc];
+      if (SPLIT3) ztlo[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_lo[lane][cc];
+    }
+    __syncthreads();
+  }
+  float wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v = rs[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int row = row0 + wy * 4 + k;
+    if (lane == 0) {
+      if (v != 0.f) atomicAdd(racc + row, (double)v);
+      if (blockIdx.y == 0) a[row] = (row < n_s) ? (1.0f / (float)n_s) : (row < n ? (-1.0f / (float)n_t) : 0.f);
+    }
+    wsum += v;
+  }
+  if (lane == 0) blk_sum[wy] = wsum;
+  __syncthreads();
+  if (wy == 0 && lane == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += blk_sum[k];
+    if (s != 0.f) atomicAdd(acc + 2, (double)s);
+  }
+}
+
+// ----------------------------------------------------------------------------- shared device helpers
+struct KernelCoefs {          // per-launch bandwidth constants, built by every thread that needs them
+  float sigma0;
+  float inv_sigma0;
+  float negc_last;            // -log2(e) / sigma_{num-1}      (fast path)
+};
+
+__device__ __forceinline__ double bandwidth_sigma0(double sum_r, int n, float mul, int num) {
+  // code/MMD.py:31-34 with sum(L) = 2 n sum_i |z_i - mean|^2
+  const double nn = (double)n;
+  double s = 2.0 * nn * sum_r / (nn * nn - nn);
+  for (int k = 0; k < num / 2; ++k) s /= (double)mul;
+  return s;
+}
+
+// sum_k exp(-L/sigma_k) and Q = sum_k exp(-L/sigma_k)/mul^k.
+// FAST: mul == 2, num == 5: one ex2 for the widest bandwidth, four squarings for the rest.
+template <bool FAST>
+__device__ __forceinline__ void kernel_terms(float L, float negc_last, const float *__restrict__ s_negc,
+                                             const float *__restrict__ s_w, int num, float &K, float &Q) {
+  if (FAST) {
+    const float e4 = ex2_approx(L * negc_last);
+    const float e3 = e4 * e4;
+    const float e2 = e3 * e3;
+    const float e1 = e2 * e2;
+    const float e0 = e1 * e1;
+    K = ((e0 + e1) + (e2 + e3)) + e4;
+    Q = fmaf(fmaf(fmaf(fmaf(e4, 0.5f, e3), 0.5f, e2), 0.5f, e1), 0.5f, e0);
+  } else {
+    K = 0.f;
+    Q = 0.f;
+    for (int k = 0; k < num; ++k) {
+      const float e = ex2_approx(L * s_negc[k]);
+      K += e;
+      Q = fmaf(e, s_w[k], Q);
+    }
+  }
+}
+
+__device__ __forceinline__ void fill_generic_coefs(float *s_negc, float *s_w, float sigma0, float mul, int num) {
+  float sk = sigma0, w = 1.f;
+  for (int k = 0; k < num; ++k) {
+    s_negc[k] = -LOG2E / sk;
+    s_w[k] = w;
+    sk *= mul;
+    w /= mul;
+  }
+}
+
+__device__ __forceinline__ void decode_tile(long long t, int nb, int &I, int &J) {
+  // upper-triangular tiles in row-major order: row I holds nb - I tiles, offset(I) = I nb - I (I-1) / 2
+  const double b = 2.0 * nb + 1.0;
+  int i = (int)floor((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+  if (i < 0) i = 0;
+  if (i > nb - 1) i = nb - 1;
+  while ((long long)i * nb - (long long)i * (i - 1) / 2 > t) --i;
+  while ((long long)(i + 1) * nb - (long long)(i + 1) * i / 2 <= t) ++i;
+  I = i;
+  J = i + (int)(t - ((long long)i * nb - (long long)i * (i - 1) / 2));
+}
+
+__device__ __forceinline__ void write_final_stats(double M, double Dsum, double sum_r, int n, float mul, int num,
+                                                  float *loss, float *stats) {
+  const double sigma0 = bandwidth_sigma0(sum_r, n, mul, num);
+  const double nn = (double)n;
+  double half = 1.0;
+  for (int k = 0; k < num / 2; ++k) half *= (double)mul;
+  const double D = (sigma0 > 0.0) ? Dsum / (sigma0 * sigma0) : 0.0;
+  const double c = D / ((nn * nn - nn) * half);
+  *loss = (float)fabs(M);
+  stats[EDRL_MMD_STAT_M] = (float)M;
+  stats[EDRL_MMD_STAT_SIGMA0] = (float)sigma0;
+  stats[EDRL_MMD_STAT_D] = (float)D;
+  stats[EDRL_MMD_STAT_C] = (float)c;
+  stats[EDRL_MMD_STAT_SUMR] = (float)sum_r;
+  stats[5] = 0.f;
+  stats[6] = 0.f;
+  stats[7] = 0.f;
+}
+
+// ----------------------------------------------------------------------------- K2: forward
+enum { MODE_LOSS = 0, MODE_KMAT = 1, MODE_GRAM = 2 };
+
+struct FwdParams {
+  int n, n_s, n_t, n_pad, d_pad, nb, kchunks, num;
+  float mul;
+  long long tiles_total;     // nb (nb + 1) / 2
+  int tile_rank, tile_world;
+  const double *racc;        // double[n_pad] row norms
+  const float *a;            // float[n_pad] block weights
+  double *acc;               // [0] M, [1] sum a a L Q, [2] sum r
+  unsigned *ticket;
+  float *loss, *stats;
+  double *partial;           // sharded evaluation: partial sums out
+  float *out;                // MODE_KMAT / MODE_GRAM: [n, n]
+};
+
+constexpr int FWD_THREADS = 320;          // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
+constexpr int FWD_EPI_THREADS = 256;
+
+template <bool SPLIT3>
+struct FwdCfg {
+  static constexpr int STAGE_BYTES = (SPLIT3 ? 4 : 2) * TILE_BYTES;
+  static constexpr int STAGES = SPLIT3 ? 3 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4096 + 1024;   // + control block + alignment slack
+};
+
+struct FwdCtrl {                 // lives after the operand ring
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+  float2 colinfo[2][BN];         // (r_j, a_j) of the current J tile, per accumulator stage
+  float negc[MAX_KERNELS];
+  float w[MAX_KERNELS];
+  double red[8][2];
+};
+
+template <bool SPLIT3, int MODE, bool FAST>
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+mmd_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const FwdParams p) {
+  using Cfg = FwdCfg<SPLIT3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FwdCtrl *ctl = reinterpret_cast<FwdCtrl *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->tmem_full[s], 1);
+      mbar_init(&ctl->tmem_empty[s], FWD_EPI_THREADS / 32);
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, 256);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_hi);
+    if (SPLIT3) tma_prefetch_desc(&tm_lo);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  // this CTA's tiles: local index q = blockIdx.x + i * gridDim.x, global tile t = tile_rank + tile_world * q
+  const long long my_first = blockIdx.x;
+  const long long q_total = (p.tiles_total - p.tile_rank + p.tile_world - 1) / p.tile_world;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long q = my_first; q < q_total; q += gridDim.x) {
+        int I, J;
+        decode_tile(p.tile_rank + p.tile_world * q, p.nb, I, J);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t *st = smem + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&ctl->full[s], Cfg::STAGE_BYTES);
+          tma_load_2d(st, &tm_hi, &ctl->full[s], kc * BK, I * BM);
+          tma_load_2d(st + TILE_BYTES, &tm_hi, &ctl->full[s], kc * BK, J * BN);
+          if (SPLIT3) {
+            tma_load_2d(st + 2 * TILE_BYTES, &tm_lo, &ctl->full[s], kc * BK, I * BM);
+            tma_load_2d(st + 3 * TILE_BYTES, &tm_lo, &ctl->full[s], kc * BK, J * BN);
+          }
+          if (++s == Cfg::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (long long q = my_first; q < q_total; q += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t u = (uint32_t)(it >> 1);
+        mbar_wait(&ctl->tmem_empty[as], (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sa + TILE_BYTES);
+          const uint64_t a_lo = make_kmajor_sw128_desc(sa + 2 * TILE_BYTES);
+          const uint64_t b_lo = make_kmajor_sw128_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+            const uint32_t first = (kc > 0 || k > 0) ? 1u : 0u;
+            if (SPLIT3) {
+              // small cross terms first, the dominant hi.hi term last
+              mma_tf32_ss(d_tmem, a_lo + adv, b_hi + adv, idesc, first);
+              mma_tf32_ss(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, first);
+            }
+          }
+          mma_commit(&ctl->empty[s]);
+          if (++s == Cfg::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        mma_commit(&ctl->tmem_full[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: 8 warps, thread = one row, warpgroup = 64 columns =====================
+    const int ew = warp - 2;                 // 0..7
+    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int ch = ew >> 2;                  // column half
+    const int et = ew * 32 + lane;           // 0..255
+    const int row = lg * 32 + lane;
+
+    const double sum_r = p.acc[2];
+    const float sigma0 = (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num);
+    float sig_last = sigma0;
+    for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
+    const float negc_last = -LOG2E / sig_last;
+    if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
+    // (the named barrier inside the tile loop orders these writes before their first use)
+
+    double accM = 0.0, accD = 0.0;
+    int it = 0;
+    for (long long q = my_first; q < q_total; q += gridDim.x, ++it) {
+      int I, J;
+      decode_tile(p.tile_rank + p.tile_world * q, p.nb, I, J);
+      const int as = it & 1;
+      const uint32_t u = (uint32_t)(it >> 1);
+      if (et < BN) {
+        const int gj = J * BN + et;
+        ctl->colinfo[as][et] = make_float2((float)p.racc[gj], p.a[gj]);
+      }
+      const int gi = I * BM + row;
+      const float ri = (float)p.racc[gi];
+      const float ai = p.a[gi];
+      named_barrier_sync(1, FWD_EPI_THREADS);
+      mbar_wait(&ctl->tmem_full[as], u & 1);
+      tc_fence_after();
+      float tM = 0.f, tD = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = ch * 64 + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * BN + col0), v);
+        tmem_ld_wait();
+        if (MODE == MODE_LOSS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 ci = ctl->colinfo[as][col0 + j];
+            float L = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
+            L = fmaxf(L, 0.f);
+            float K, Q;
+            kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+            tM = fmaf(ci.y, K, tM);
+            tD = fmaf(ci.y * L, Q, tD);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j) {
+            const int gj = J * BN + col0 + j;
+            float val;
+            if (MODE == MODE_GRAM) {
+              val = __uint_as_float(v[j]);
+            } else {
+              const float2 ci = ctl->colinfo[as][col0 + j];
+              float L = fmaxf(fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x), 0.f);
+              float Q;
+              kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, val, Q);
+            }
+            if (gi < p.n && gj < p.n) {
+              p.out[(size_t)gi * p.n + gj] = val;
+              if (I != J) p.out[(size_t)gj * p.n + gi] = val;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->tmem_empty[as]);
+      if (MODE == MODE_LOSS) {
+        const float wgt = (I == J) ? ai : 2.f * ai;
+        accM += (double)(wgt * tM);
+        accD += (double)(wgt * tD);
+      }
+    }
+    if (MODE == MODE_LOSS) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        accM += __shfl_xor_sync(0xffffffffu, accM, o);
+        accD += __shfl_xor_sync(0xffffffffu, accD, o);
+      }
+      if (lane == 0) {
+        ctl->red[ew][0] = accM;
+        ctl->red[ew][1] = accD;
+      }
+      named_barrier_sync(1, FWD_EPI_THREADS);
+      if (et == 0) {
+        double m = 0.0, dd = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          m += ctl->red[k][0];
+          dd += ctl->red[k][1];
+        }
+        atomicAdd(p.acc + 0, m);
+        atomicAdd(p.acc + 1, dd);
+        __threadfence();
+        const unsigned t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+          __threadfence();
+          const double M = atomicAdd(p.acc + 0, 0.0);
+          const double Ds = atomicAdd(p.acc + 1, 0.0);
+          if (p.partial) {
+            p.partial[0] = M;
+            p.partial[1] = Ds;
+          }
+          if (p.tile_world == 1) write_final_stats(M, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+__global__ void mmd_finalize_kernel(const double *partial, const double *acc, int n, float mul, int num, float *loss,
+                                    float *stats) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) write_final_stats(partial[0], partial[1], acc[2], n, mul, num, loss, stats);
+}
+
+// ----------------------------------------------------------------------------- K3: backward
+constexpr int DC = 256;                       // columns of dZ one CTA accumulates in TMEM
+constexpr int BWD_THREADS = 320;
+constexpr int BWD_EPI_THREADS = 256;
+constexpr int BWD_STAGE_BYTES = 2 * TILE_BYTES;   // A chunk + B chunk, or one 256 x 32 chunk of Z^T
+constexpr int G_BYTES = BM * BN * 4;          // 64 KiB, four 128-byte-swizzle K atoms
+
+template <bool SPLIT3>
+struct BwdCfg {
+  // SPLIT3 keeps G as hi + lo (2 x 64 KiB) and therefore a shorter operand ring (each step of
+  // the 3xTF32 product needs a hi stage and a lo stage resident together).
+  static constexpr int STAGES = SPLIT3 ? 2 : 4;
+  static constexpr int G_TOTAL = SPLIT3 ? 2 * G_BYTES : G_BYTES;
+  static constexpr int CTRL_BYTES = 6144;
+  static constexpr int SMEM_BYTES = STAGES * BWD_STAGE_BYTES + G_TOTAL + CTRL_BYTES + 1024;
+};
+
+struct BwdCtrl {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t s_full[2];
+  uint64_t s_empty[2];
+  uint64_t g_full;
+  uint64_t g_empty;
+  uint64_t dz_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+  float4 colinfo[2][BN];          // (r_j, a_j, c_j, -) per S stage
+  float negc[MAX_KERNELS];
+  float w[MAX_KERNELS];
+  float rowsum[2][BM];
+};
+
+static_assert(sizeof(BwdCtrl) <= 6144, "BwdCtrl does not fit its smem slot");
+static_assert(sizeof(FwdCtrl) <= 4096, "FwdCtrl does not fit its smem slot");
+
+struct BwdParams {
+  int n, n_s, n_pad, d, d_pad, nb, kchunks, num;
+  float mul;
+  int row_begin, row_count;
+  const double *racc;
+  const float *a;
+  const float *zhi, *zlo;          // [n_pad, d_pad]
+  const float *stats;
+  const float *grad_out;
+  float *dz;                       // [row_count, d]
+};
+
+// ring order (producer and MMA issuer walk the same sequence):
+//   S(0) chunks | for J: S(J+1) chunks (if any), Z^T(J) chunks
+// SPLIT3 chunks: S -> (A_hi,B_hi), (A_lo,B_lo) per K chunk; Z^T -> hi chunk, lo chunk per 32 columns of J.
+template <bool SPLIT3, bool FAST>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+mmd_bwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const __grid_constant__ CUtensorMap tm_thi, const __grid_constant__ CUtensorMap tm_tlo,
+               const BwdParams p) {
+  using Cfg = BwdCfg<SPLIT3>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *g_smem = smem + Cfg::STAGES * BWD_STAGE_BYTES;
+  BwdCtrl *ctl = reinterpret_cast<BwdCtrl *>(g_smem + Cfg::G_TOTAL);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row_base = p.row_begin + blockIdx.x * BM;      // first global row of this panel
+  const int f0 = blockIdx.y * DC;                           // first feature column of this slice
+  const int nJ = p.nb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->s_full[s], 1);
+      mbar_init(&ctl->s_empty[s], BWD_EPI_THREADS / 32);
+    }
+    mbar_init(&ctl->g_full, BWD_EPI_THREADS);
+    mbar_init(&ctl->g_empty, 1);
+    mbar_init(&ctl->dz_full, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(&ctl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_thi);
+    if (SPLIT3) {
+      tma_prefetch_desc(&tm_lo);
+      tma_prefetch_desc(&tm_tlo);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_dz = tmem_base;              // columns [0, 256)
+  const uint32_t tmem_s = tmem_base + DC;          // two S stages of 128 columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      auto next = [&]() {
+        if (++s == Cfg::STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      };
+      auto load_S = [&](int J) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t *st = smem + s * BWD_STAGE_BYTES;
+          mbar_expect_tx(&ctl->full[s], BWD_STAGE_BYTES);
+          tma_load_2d(st, &tm_hi, &ctl->full[s], kc * BK, row_base);
+          tma_load_2d(st + TILE_BYTES, &tm_hi, &ctl->full[s], kc * BK, J * BN);
+          next();
+          if (SPLIT3) {
+            mbar_wait(&ctl->empty[s], ph ^ 1);
+            st = smem + s * BWD_STAGE_BYTES;
+            mbar_expect_tx(&ctl->full[s], BWD_STAGE_BYTES);
+            tma_load_2d(st, &tm_lo, &ctl->full[s], kc * BK, row_base);
+            tma_load_2d(st + TILE_BYTES, &tm_lo, &ctl->full[s], kc * BK, J * BN);
+            next();
+          }
+        }
+      };
+      auto load_Zt = [&](int J) {
+        for (int a4 = 0; a4 < BN / BK; ++a4) {
+          mbar_wait(&ctl->empty[s], ph ^ 1);
+          uint8_t *st = smem + s * BWD_STAGE_BYTES;
+          mbar_expect_tx(&ctl->full[s], BWD_STAGE_BYTES);
+          tma_load_2d(st, &tm_thi, &ctl->full[s], J * BN + a4 * BK, f0);
+          next();
+          if (SPLIT3) {
+            mbar_wait(&ctl->empty[s], ph ^ 1);
+            st = smem + s * BWD_STAGE_BYTES;
+            mbar_expect_tx(&ctl->full[s], BWD_STAGE_BYTES);
+            tma_load_2d(st, &tm_tlo, &ctl->full[s], J * BN + a4 * BK, f0);
+            next();
+          }
+        }
+      };
+      load_S(0);
+      for (int J = 0; J < nJ; ++J) {
+        if (J + 1 < nJ) load_S(J + 1);
+        load_Zt(J);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc_p = make_idesc_tf32(BM, DC);
+      int s = 0;
+      uint32_t ph = 0;
+      auto next = [&]() {
+        if (++s == Cfg::STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      };
+      auto issue_S = [&](int J) {
+        const int b = J & 1;
+        const uint32_t u = (uint32_t)(J >> 1);
+        mbar_wait(&ctl->s_empty[b], (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_s + b * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * BWD_STAGE_BYTES);
+          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sa + TILE_BYTES);
+          if (!SPLIT3) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc_s, (kc > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&ctl->empty[s]);
+            next();
+          } else {
+            // stage s: (A_hi, B_hi); stage s+1: (A_lo, B_lo)
+            const int s_hi = s;
+            next();
+            mbar_wait(&ctl->full[s], ph);
+            tc_fence_after();
+            const uint32_t sl = smem_u32(smem + s * BWD_STAGE_BYTES);
+            const uint64_t a_lo = make_kmajor_sw128_desc(sl);
+            const uint64_t b_lo = make_kmajor_sw128_desc(sl + TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss(d_tmem, a_lo + adv, b_hi + adv, idesc_s, (kc > 0 || k > 0) ? 1u : 0u);
+              mma_tf32_ss(d_tmem, a_hi + adv, b_lo + adv, idesc_s, 1u);
+              mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc_s, 1u);
+            }
+            mma_commit(&ctl->empty[s_hi]);
+            mma_commit(&ctl->empty[s]);
+            next();
+          }
+        }
+        mma_commit(&ctl->s_full[b]);
+      };
+      auto issue_P = [&](int J) {
+        mbar_wait(&ctl->g_full, (uint32_t)(J & 1));
+        tc_fence_after();
+        const uint32_t g_hi = smem_u32(g_smem);
+        const uint32_t g_lo = g_hi + G_BYTES;
+        for (int a4 = 0; a4 < BN / BK; ++a4) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          const uint64_t a_hi = make_kmajor_sw128_desc(g_hi + a4 * TILE_BYTES);
+          const uint64_t b_hi = make_kmajor_sw128_desc(smem_u32(smem + s * BWD_STAGE_BYTES));
+          if (!SPLIT3) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss(tmem_dz, a_hi + adv, b_hi + adv, idesc_p, (J > 0 || a4 > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(&ctl->empty[s]);
+            next();
+          } else {
+            const int s_hi = s;
+            next();
+            mbar_wait(&ctl->full[s], ph);
+            tc_fence_after();
+            const uint64_t a_lo = make_kmajor_sw128_desc(g_lo + a4 * TILE_BYTES);
+            const uint64_t b_lo = make_kmajor_sw128_desc(smem_u32(smem + s * BWD_STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss(tmem_dz, a_lo + adv, b_hi + adv, idesc_p, (J > 0 || a4 > 0 || k > 0) ? 1u : 0u);
+              mma_tf32_ss(tmem_dz, a_hi + adv, b_lo + adv, idesc_p, 1u);
+              mma_tf32_ss(tmem_dz, a_hi + adv, b_hi + adv, idesc_p, 1u);
+            }
+            mma_commit(&ctl->empty[s_hi]);
+            mma_commit(&ctl->empty[s]);
+            next();
+          }
+        }
+        mma_commit(&ctl->g_empty);
+      };
+      issue_S(0);
+      for (int J = 0; J < nJ; ++J) {
+        if (J + 1 < nJ) issue_S(J + 1);
+        issue_P(J);
+      }
+      mma_commit(&ctl->dz_full);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int ch = ew >> 2;
+    const int et = ew * 32 + lane;
+    const int row = lg * 32 + lane;
+    const int gi = row_base + row;
+    const bool row_ok = (row < p.row_count - blockIdx.x * BM) && gi < p.n;
+
+    const float M = p.stats[EDRL_MMD_STAT_M];
+    const float sigma0 = p.stats[EDRL_MMD_STAT_SIGMA0];
+    const float cval = p.stats[EDRL_MMD_STAT_C];
+    float sig_last = sigma0;
+    for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
+    const float negc_last = -LOG2E / sig_last;
+    if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
+
+    const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
+    const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
+    const float nai_sig = -ai / sigma0;
+    float rowsum = 0.f;
+
+    for (int J = 0; J < nJ; ++J) {
+      const int b = J & 1;
+      const uint32_t u = (uint32_t)(J >> 1);
+      if (et < BN) {
+        const int gj = J * BN + et;
+        ctl->colinfo[b][et] = make_float4((float)p.racc[gj], p.a[gj], (gj < p.n) ? cval : 0.f, 0.f);
+      }
+      named_barrier_sync(1, BWD_EPI_THREADS);
+      mbar_wait(&ctl->s_full[b], u & 1);
+      tc_fence_after();
+      // G buffer must have been consumed by the P-MMA of tile J-1
+      mbar_wait(&ctl->g_empty, (uint32_t)((J & 1) ^ 1));
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = ch * 64 + c * 32;          // 32 columns == one swizzle atom of G
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * BN + col0), v);
+        tmem_ld_wait();
+        float g[32];
+        float glo[SPLIT3 ? 32 : 1];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 ci = ctl->colinfo[b][col0 + j];
+          const float Lraw = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
+          const float L = fmaxf(Lraw, 0.f);
+          float K, Q;
+          kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+          float gv = fmaf(ci.y * Q, nai_sig, ci.z);
+          gv = (Lraw >= 0.f) ? gv : 0.f;
+          const float gh = to_tf32(gv);
+          g[j] = gh;
+          if (SPLIT3) {
+            const float gl = to_tf32(gv - gh);
+            glo[j] = gl;
+            rowsum += gh + gl;
+          } else {
+            rowsum += gh;
+          }
+        }
+        // store this thread's 32 values of row `row` into K-atom (col0 / 32), 128-byte swizzle
+        uint8_t *atom = g_smem + (col0 >> 5) * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float4 val = make_float4(g[q4 * 4 + 0], g[q4 * 4 + 1], g[q4 * 4 + 2], g[q4 * 4 + 3]);
+          *reinterpret_cast<float4 *>(atom + ((q4 ^ (row & 7)) << 4)) = val;
+          if (SPLIT3) {
+            float4 vl = make_float4(glo[q4 * 4 + 0], glo[q4 * 4 + 1], glo[q4 * 4 + 2], glo[q4 * 4 + 3]);
+            *reinterpret_cast<float4 *>(atom + G_BYTES + ((q4 ^ (row & 7)) << 4)) = vl;
+          }
+        }
+      }
+      // S stage may be overwritten; G is visible to the tensor core (async proxy)
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&ctl->g_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->s_empty[b]);
+    }
+
+    // ---- final: dZ = coef * (rowsum * z_i - P) ----
+    ctl->rowsum[ch][row] = rowsum;
+    named_barrier_sync(1, BWD_EPI_THREADS);
+    const float rs_total = ctl->rowsum[0][row] + ctl->rowsum[1][row];
+    const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
+    const float coef = 4.f * sgn * p.grad_out[0];
+    mbar_wait(&ctl->dz_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      const int col0 = ch * 128 + c * 32;
+      if (f0 + col0 >= p.d) break;              // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_dz + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const float *zr = p.zhi + (size_t)gi * p.d_pad + f0 + col0;
+        const float *zl = SPLIT3 ? (p.zlo + (size_t)gi * p.d_pad + f0 + col0) : nullptr;
+        float *out = p.dz + (size_t)(gi - p.row_begin) * p.d + f0 + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (f0 + col0 + j < p.d) {
+            float zv = zr[j];
+            if (SPLIT3) zv += zl[j];
+            out[j] = coef * fmaf(rs_total, zv, -__uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, const Layout &L, uint8_t *ws,
+                    cudaStream_t st) {
+  EDRL_CUDA_OK(cudaMemsetAsync(ws + L.off_acc, 0, L.zero_bytes, st));
+  const int n = L.n;
+  double *acc = reinterpret_cast<double *>(ws + L.off_acc);
+  double *colsum = reinterpret_cast<double *>(ws + L.off_colsum);
+  double *racc = reinterpret_cast<double *>(ws + L.off_r);
+  float *a = reinterpret_cast<float *>(ws + L.off_a);
+  float *zhi = reinterpret_cast<float *>(ws + L.off_zhi);
+  float *zthi = reinterpret_cast<float *>(ws + L.off_zthi);
+  float *zlo = reinterpret_cast<float *>(ws + L.off_zlo);
+  float *ztlo = reinterpret_cast<float *>(ws + L.off_ztlo);
+  dim3 g1((d + 127) / 128, (n + 63) / 64);
+  prep_colsum_kernel<<<g1, 128, 0, st>>>(X, Y, n_s, n, d, colsum);
+  EDRL_LAUNCHED();
+  const int rb = L.n_pad / 32;
+  int nsplit = (296 + rb - 1) / rb;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > L.d_pad / 32) nsplit = L.d_pad / 32;
+  dim3 g2(rb, nsplit), b2(32, 8);
+  if (L.split3)
+    prep_center_kernel<true><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
+                                                 racc, a, acc);
+  else
+    prep_center_kernel<false><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
+                                                  racc, a, acc);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+static int check_common(int n_s, int n_t, int d, float mul, int num, const Layout &L, const void *ws,
+                        size_t ws_bytes) {
+  EDRL_CHECK_ARG(n_s > 0 && n_t > 0 && d > 0, "MK_MMD: empty input (n_s=%d n_t=%d d=%d)", n_s, n_t, d);
+  EDRL_CHECK_ARG((long long)n_s + n_t >= 2, "MK_MMD: needs at least two samples");
+  EDRL_CHECK_ARG(num >= 1 && num <= MAX_KERNELS, "MK_MMD: kernel_num must be in [1, %d], got %d", MAX_KERNELS, num);
+  EDRL_CHECK_ARG(mul > 0.f, "MK_MMD: kernel_mul must be positive");
+  EDRL_CHECK_ARG(ws != nullptr && ws_bytes >= L.total, "MK_MMD: workspace too small (%zu < %zu)", ws_bytes, L.total);
+  EDRL_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "MK_MMD: workspace must be 1024-byte aligned");
+  return 0;
+}
+
+template <bool SPLIT3, int MODE, bool FAST>
+static int launch_fwd_t(const CUtensorMap &tm_hi, const CUtensorMap &tm_lo, const FwdParams &p, int grid,
+                        cudaStream_t st) {
+  using Cfg = FwdCfg<SPLIT3>;
+  auto kern = mmd_fwd_kernel<SPLIT3, MODE, FAST>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_hi, tm_lo, p);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+template <int MODE>
+static int launch_fwd(bool split3, bool fast, const CUtensorMap &tm_hi, const CUtensorMap &tm_lo, const FwdParams &p,
+                      int grid, cudaStream_t st) {
+  if (split3) {
+    if (fast) return launch_fwd_t<true, MODE, true>(tm_hi, tm_lo, p, grid, st);
+    return launch_fwd_t<true, MODE, false>(tm_hi, tm_lo, p, grid, st);
+  }
+  if (fast) return launch_fwd_t<false, MODE, true>(tm_hi, tm_lo, p, grid, st);
+  return launch_fwd_t<false, MODE, false>(tm_hi, tm_lo, p, grid, st);
+}
+
+static int forward_impl(int mode, const float *X, const float *Y, int n_s, int n_t, int d, float mul, int num,
+                        int flags, int tile_rank, int tile_world, float *loss, float *stats, double *partial,
+                        float *out, void *workspace, size_t ws_bytes, void *stream) {
+  Layout L = make_layout(n_s, n_t, d, flags);
+  if (int rc = check_common(n_s, n_t, d, mul, num, L, workspace, ws_bytes)) return rc;
+  EDRL_CHECK_ARG(tile_world >= 1 && tile_rank >= 0 && tile_rank < tile_world, "MK_MMD: bad tile shard %d/%d",
+                 tile_rank, tile_world);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  if (int rc = run_prep(X, Y, n_s, n_t, d, L, ws, st)) return rc;
+
+  CUtensorMap tm_hi, tm_lo;
+  if (int rc = make_tmap_2d_f32(&tm_hi, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
+  if (L.split3) {
+    if (int rc = make_tmap_2d_f32(&tm_lo, ws + L.off_zlo, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
+  } else {
+    tm_lo = tm_hi;
+  }
+  FwdParams p;
+  p.n = L.n; p.n_s = n_s; p.n_t = n_t; p.n_pad = L.n_pad; p.d_pad = L.d_pad;
+  p.nb = L.n_pad / BM; p.kchunks = L.d_pad / BK; p.num = num; p.mul = mul;
+  p.tiles_total = (long long)p.nb * (p.nb + 1) / 2;
+  p.tile_rank = tile_rank; p.tile_world = tile_world;
+  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
+  p.a = reinterpret_cast<const float *>(ws + L.off_a);
+  p.acc = reinterpret_cast<double *>(ws + L.off_acc);
+  p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
+  p.loss = loss; p.stats = stats; p.partial = partial; p.out = out;
+  const long long q_total = (p.tiles_total - tile_rank + tile_world - 1) / tile_world;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  int grid = (int)((q_total < sms) ? (q_total > 0 ? q_total : 1) : sms);
+  const bool fast = (mul == 2.0f && num == 5);
+  if (mode == MODE_LOSS) return launch_fwd<MODE_LOSS>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
+  if (mode == MODE_KMAT) return launch_fwd<MODE_KMAT>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
+  return launch_fwd<MODE_GRAM>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
+}
+
+template <bool SPLIT3, bool FAST>
+static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &c, const CUtensorMap &d4,
+                        const BwdParams &p, dim3 grid, cudaStream_t st) {
+  using Cfg = BwdCfg<SPLIT3>;
+  auto kern = mmd_bwd_kernel<SPLIT3, FAST>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, c, d4, p);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+}  // namespace mmd
+}  // namespace edrl
+
+using namespace edrl;
+using namespace edrl::mmd;
+
+extern "C" {
+
+size_t edrl_mmd_workspace_bytes(int n_s, int n_t, int d, int flags) {
+  if (n_s <= 0 || n_t <= 0 || d <= 0) return 0;
+  return make_layout(n_s, n_t, d, flags).total;
+}
+
+int edrl_mmd_forward(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
+                     int flags, int tile_rank, int tile_world, float *loss, float *stats, double *partial,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_CHECK_ARG(X && Y, "MK_MMD: null input");
+  EDRL_CHECK_ARG(tile_world > 1 ? partial != nullptr : (loss && stats), "MK_MMD: null output");
+  return forward_impl(MODE_LOSS, X, Y, n_s, n_t, d, kernel_mul, kernel_num, flags, tile_rank, tile_world, loss, stats,
+                      partial, nullptr, workspace, workspace_bytes, stream);
+}
+
+int edrl_mmd_finalize(const double *partial, int n_s, int n_t, float kernel_mul, int kernel_num, float *loss,
+                      float *stats, void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_CHECK_ARG(partial && loss && stats && workspace, "edrl_mmd_finalize: null argument");
+  EDRL_CHECK_ARG(workspace_bytes >= 256, "edrl_mmd_finalize: workspace too small");
+  mmd_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partial, reinterpret_cast<const double *>(workspace), n_s + n_t, kernel_mul, kernel_num, loss, stats);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+int edrl_mmd_kernel_matrix(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
+                           int flags, float *K, void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_CHECK_ARG(X && Y && K, "gaussian_kernel: null argument");
+  const int mode = (flags & 0x100) ? MODE_GRAM : MODE_KMAT;   // 0x100: debug, raw centred Gram
+  return forward_impl(mode, X, Y, n_s, n_t, d, kernel_mul, kernel_num, flags & 0xff, 0, 1, nullptr, nullptr, nullptr,
+                      K, workspace, workspace_bytes, stream);
+}
+
+int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num, int flags, const float *stats,
+                      const float *grad_out, int row_begin, int row_count, float *dZ, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+  Layout L = make_layout(n_s, n_t, d, flags);
+  if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
+  EDRL_CHECK_ARG(stats && grad_out && dZ, "MK_MMD backward: null argument");
+  EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n,
+                 "MK_MMD backward: row range [%d, %d) outside [0, %d)", row_begin, row_begin + row_count, L.n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  CUtensorMap tm_hi, tm_lo, tm_thi, tm_tlo;
+  if (int rc = make_tmap_2d_f32(&tm_hi, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
+  if (int rc = make_tmap_2d_f32(&tm_thi, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, DC, BK)) return rc;
+  if (L.split3) {
+    if (int rc = make_tmap_2d_f32(&tm_lo, ws + L.off_zlo, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
+    if (int rc = make_tmap_2d_f32(&tm_tlo, ws + L.off_ztlo, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, DC, BK))
+      return rc;
+  } else {
+    tm_lo = tm_hi;
+    tm_tlo = tm_thi;
+  }
+  BwdParams p;
+  p.n = L.n; p.n_s = n_s; p.n_pad = L.n_pad; p.d = d; p.d_pad = L.d_pad;
+  p.nb = L.n_pad / BN; p.kchunks = L.d_pad / BK; p.num = kernel_num; p.mul = kernel_mul;
+  p.row_begin = row_begin; p.row_count = row_count;
+  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
+  p.a = reinterpret_cast<const float *>(ws + L.off_a);
+  p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  p.zlo = reinterpret_cast<const float *>(ws + L.off_zlo);
+  p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
+  dim3 grid((row_count + BM - 1) / BM, (d + DC - 1) / DC);
+  const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
+  if (L.split3) {
+    if (fast) return launch_bwd_t<true, true>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+    return launch_bwd_t<true, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+  }
+  if (fast) return launch_bwd_t<false, true>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+  return launch_bwd_t<false, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+}
+
+}  // extern "C"

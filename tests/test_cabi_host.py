@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/edrl_b200.h declares,
+the ctypes prototypes cover the header, and the product path has no CPU fallback."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "edrl_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(edrl_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    ge.build()
+    import edrl_b200
+    return edrl_b200
+
+
+def test_header_symbols_exported_and_bound(pkg):
+    names = _declared()
+    assert len(names) >= 22
+    lib = pkg._lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(pkg._lib.PROTOTYPES) == names
+    assert lib.edrl_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (edrl_[a-z0-9_]+)", out))
+    assert exported == set(names)
+
+
+def test_workspace_bytes_is_pure_host_logic(pkg):
+    lib = pkg._lib.load()
+    assert lib.edrl_mmd_workspace_bytes(0, 4, 8, 0) == 0
+    small = lib.edrl_mmd_workspace_bytes(4, 4, 8, 0)
+    assert small >= 2 * 128 * 32 * 4
+    assert lib.edrl_mmd_workspace_bytes(4, 4, 8, 1) > small                     # hi + lo operands
+    big = lib.edrl_mmd_workspace_bytes(8192, 8192, 512, 0)
+    assert 2 * 16384 * 512 * 4 <= big <= 2 * 16384 * 512 * 4 + (1 << 20)
+
+
+def test_sass_is_blackwell_native(pkg):
+    """tcgen05 MMA / TMEM loads / TMA in the SASS of the shipped library (B200_PROFILING.md table)."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass or re.search(r"UTC\w*MMA", sass)
+    assert "LDTM" in sass
+    assert "UTMALDG" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")          # no legacy mma.sync path
+
+
+def test_no_cpu_fallback(pkg):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.MK_MMD(torch.randn(4, 8), torch.randn(4, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pkg.topk_rows(torch.randn(4, 8), 2)
+    m = pkg.EPRL(16, z_dim=8, sample_num=120, num_classes=2, batch_size=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 5, 16), torch.tensor([0, 1]))
+    # the product never imports the oracle
+    for mod in list(sys.modules):
+        assert not (mod.startswith("edrl_b200") and "oracle" in mod)
+    pkg_dir = os.path.dirname(pkg.__file__)
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg_dir, fn)).read().replace("the oracle", "")
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch, tmp_path):
+    monkeypatch.setattr(pkg._lib, "_lib", None)
+    monkeypatch.setattr(pkg._lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="missing"):
+        pkg._lib.load()
+
+
+def test_state_dict_names_match_reference(pkg, golden_dir):
+    import numpy as np
+    ge = np.load(os.path.join(golden_dir, "eprl_reference.npz"))
+    m = pkg.EPRL(1024, num_classes=2, sample_num=800, batch_size=4)
+    sd = m.state_dict()
+    assert sorted(sd.keys()) == sorted(ge["state_dict_keys"].tolist())
+    shapes = dict(zip(ge["state_dict_keys"].tolist(), ge["state_dict_shapes"].tolist()))
+    for k, v in sd.items():
+        assert str(tuple(v.shape)) == shapes[k]

@@ -1,0 +1,249 @@
+"""GPU parity tests, Part A (MK_MMD): the sm_100a kernels, called through the C-ABI / the host
+package, against the numpy oracle and the committed reference-generated golden vectors.
+
+Tolerances (written here as the contract):
+  3xTF32 mode : loss rtol 1e-4 (+ atol 1e-6), gradients 1e-4 * |grad|_inf absolute
+  TF32 mode   : loss rtol 1e-3 (+ atol 1e-6), gradients 2e-3 * |grad|_inf absolute
+against the fp64 reference/oracle value.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import RawMMD, dev, have_gpu, tf32_round
+from oracle import edrl_oracle as O
+from oracle.gen_golden import MMD_CASES, MMD_VARIANTS, mmd_inputs
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_gpu(), reason="needs a CUDA device")]
+
+MODES = [("3xtf32", 1, 1e-4, 1e-4), ("tf32", 0, 1e-3, 2e-3)]   # name, flag, loss rtol, grad atol / |g|_inf
+
+
+@pytest.fixture(scope="module")
+def raw():
+    return RawMMD()
+
+
+@pytest.fixture(scope="module")
+def gm(golden_dir):
+    return np.load(os.path.join(golden_dir, "mmd_reference.npz"))
+
+
+def _case(case):
+    x, y = mmd_inputs(*case)
+    return x.numpy(), y.numpy()
+
+
+# ---------------------------------------------------------------- plumbing: TMA -> tcgen05 -> TMEM
+@pytest.mark.parametrize("ns,nt,d", [(4, 4, 8), (37, 53, 24), (128, 128, 32), (130, 200, 100), (256, 256, 512)])
+@pytest.mark.parametrize("flag", [0, 1])
+def test_centred_gram_tiles(raw, ns, nt, d, flag):
+    rng = np.random.default_rng(ns * 1000 + d)
+    x = rng.standard_normal((ns, d)).astype(np.float32)
+    y = (rng.standard_normal((nt, d)) * 1.3 + 0.2).astype(np.float32)
+    g = raw.kernel_matrix(dev(x), dev(y), flags=flag | 0x100).cpu().numpy().astype(np.float64)
+    z = np.concatenate([x, y]).astype(np.float64)
+    zc = (z - z.mean(0)).astype(np.float32)
+    if flag == 0:
+        zr = tf32_round(zc).astype(np.float64)
+        ref = zr @ zr.T
+        tol = 2e-5
+    else:
+        ref = zc.astype(np.float64) @ zc.astype(np.float64).T
+        tol = 2e-5
+    scale = np.abs(ref).max()
+    # the device centres with an fp64 column mean rounded to fp32; allow that rounding too
+    assert np.abs(g - ref).max() <= tol * scale + 1e-6 * scale, np.abs(g - ref).max() / scale
+    np.testing.assert_array_equal(g, g.T)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+def test_gaussian_kernel_matrix(raw, mode):
+    import edrl_b200
+    x, y = _case(MMD_CASES[3])
+    k = edrl_b200.gaussian_kernel(dev(x), dev(y), precision=mode[0]).cpu().numpy()
+    ref = O.gaussian_kernel(x, y)
+    assert k.shape == ref.shape
+    np.testing.assert_allclose(k, ref, rtol=mode[2] * 10, atol=mode[2])
+    # hand-checkable case of SURVEY.md section 4
+    xh = np.array([[0.0], [1.0]]); yh = np.array([[2.0], [3.0]])
+    kh = edrl_b200.gaussian_kernel(dev(xh), dev(yh), precision=mode[0]).cpu().numpy()
+    np.testing.assert_allclose(kh[0], [5.0, 3.37927553, 1.68977177, 0.84013917], rtol=2e-3)
+
+
+# ---------------------------------------------------------------- known-answer table (reference-generated)
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+@pytest.mark.parametrize("case", MMD_CASES, ids=lambda c: f"seed{c[0]}")
+def test_mk_mmd_kat_forward_backward(case, mode, gm):
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    seed = case[0]
+    x, y = _case(case)
+    xt = dev(x).requires_grad_(True)
+    yt = dev(y).requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, precision=name)
+    assert loss.dim() == 0 and loss.device.type == "cuda" and loss.dtype == torch.float32
+    loss.backward()
+    ref = float(gm[f"s{seed}_loss64"])
+    assert np.isclose(loss.item(), ref, rtol=ltol, atol=1e-6), (loss.item(), ref)
+    _, _, dx, dy = O.mk_mmd_grad(x, y)
+    gmax = float(gm[f"s{seed}_maxabs_g64"])
+    gx = xt.grad.cpu().numpy().astype(np.float64)
+    gy = yt.grad.cpu().numpy().astype(np.float64)
+    assert np.abs(gx - dx).max() <= gtol * gmax, np.abs(gx - dx).max() / gmax
+    assert np.abs(gy - dy).max() <= gtol * gmax, np.abs(gy - dy).max() / gmax
+    # the committed reference gradients themselves (strided subsample)
+    rs, rt, cs = gm[f"s{seed}_sub_strides"]
+    assert np.abs(gx[::rs, ::cs] - gm[f"s{seed}_gx64_sub"]).max() <= gtol * gmax
+    assert np.abs(gy[::rt, ::cs] - gm[f"s{seed}_gy64_sub"]).max() <= gtol * gmax
+    assert np.isclose(np.abs(gx).sum(), float(gm[f"s{seed}_sumabs_gx64"]), rtol=max(gtol, 1e-3))
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+@pytest.mark.parametrize("mul,num", MMD_VARIANTS)
+def test_mk_mmd_kernel_variants(mul, num, mode, gm):
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    x, y = _case(MMD_CASES[3])
+    xt = dev(x).requires_grad_(True)
+    yt = dev(y).requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, kernel_mul=mul, kernel_num=num, precision=name)
+    (2.5 * loss).backward()
+    key = f"var_m{mul}_k{num}"
+    assert np.isclose(loss.item(), float(gm[key + "_loss"]), rtol=ltol, atol=1e-6)
+    gmax = max(np.abs(gm[key + "_gx"]).max(), np.abs(gm[key + "_gy"]).max()) * 2.5
+    assert np.abs(xt.grad.cpu().numpy() - 2.5 * gm[key + "_gx"]).max() <= gtol * gmax
+    assert np.abs(yt.grad.cpu().numpy() - 2.5 * gm[key + "_gy"]).max() <= gtol * gmax
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+def test_mk_mmd_edge_cases(mode, gm):
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    # hand case
+    xh = dev(np.array([[0.0], [1.0]])); yh = dev(np.array([[2.0], [3.0]]))
+    assert np.isclose(edrl_b200.MK_MMD(xh, yh, precision=name).item(), 4.579796409474792, rtol=ltol)
+    # identical inputs: loss 0, zero gradient (up to fp32 cancellation)
+    xi, _ = mmd_inputs(7, 6, 6, 5, 0, 1)
+    a = dev(xi.numpy()).requires_grad_(True)
+    b = dev(xi.numpy()).requires_grad_(True)
+    l = edrl_b200.MK_MMD(a, b, precision=name)
+    l.backward()
+    assert abs(l.item()) <= 1e-6
+    assert a.grad.abs().max().item() <= 1e-5 and b.grad.abs().max().item() <= 1e-5
+    # one-sided gradient requests and duplicate rows (clamp path)
+    x, y = _case(MMD_CASES[3])
+    x[5] = x[4]
+    y[7] = x[4]
+    xt = dev(x).requires_grad_(True)
+    l = edrl_b200.MK_MMD(xt, dev(y), precision=name)
+    l.backward()
+    ref_l, _, dx, _ = O.mk_mmd_grad(x, y)
+    assert np.isclose(l.item(), ref_l, rtol=ltol, atol=1e-6)
+    assert np.abs(xt.grad.cpu().numpy() - dx).max() <= gtol * np.abs(dx).max()
+    yt = dev(y).requires_grad_(True)
+    l = edrl_b200.MK_MMD(dev(x), yt, precision=name)
+    l.backward()
+    _, _, _, dy = O.mk_mmd_grad(x, y)
+    assert np.abs(yt.grad.cpu().numpy() - dy).max() <= gtol * np.abs(dy).max()
+    # fp64 inputs: computed in fp32, cast back
+    l64 = edrl_b200.MK_MMD(dev(x, torch.float64), dev(y, torch.float64), precision=name)
+    assert l64.dtype == torch.float64 and np.isclose(l64.item(), ref_l, rtol=ltol, atol=1e-6)
+
+
+def test_mk_mmd_errors():
+    import edrl_b200
+    with pytest.raises(RuntimeError):
+        edrl_b200.MK_MMD(torch.randn(4, 8), torch.randn(4, 8))             # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        edrl_b200.MK_MMD(torch.randn(4, 8).cuda(), torch.randn(4, 9).cuda())
+    with pytest.raises(ValueError):
+        edrl_b200.MK_MMD(torch.randn(4, 8).cuda(), torch.randn(4, 8).cuda(), kernel_num=0)
+    with pytest.raises(ValueError):
+        edrl_b200.MK_MMD(torch.randn(4, 8).cuda(), torch.randn(4, 8).cuda(), precision="fp8")
+
+
+# ---------------------------------------------------------------- C-ABI details: row ranges, tile shards
+@pytest.mark.parametrize("flag", [0, 1])
+def test_backward_row_ranges_and_tile_shards(raw, flag):
+    ns, nt, d = 300, 212, 96
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((ns, d)).astype(np.float32)
+    y = (rng.standard_normal((nt, d)) * 1.2 + 0.1).astype(np.float32)
+    xd, yd = dev(x), dev(y)
+    loss, stats, _, ws = raw.forward(xd, yd, flags=flag)
+    full = raw.backward(ns, nt, d, stats, ws, 0, ns + nt, flags=flag)
+    part = raw.backward(ns, nt, d, stats, ws, 131, 257, grad_out=1.0, flags=flag)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(part.cpu().numpy(), full[131:131 + 257].cpu().numpy(), rtol=0, atol=0)
+    # upper-triangular tile list split over 3 "ranks": partial sums add up to the single-rank result
+    tot = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for r in range(3):
+        _, _, p, ws_r = raw.forward(xd, yd, flags=flag, tile_rank=r, tile_world=3)
+        tot += p
+    l2, s2 = raw.finalize(tot, ns, nt, ws_r)
+    torch.cuda.synchronize()
+    assert np.isclose(l2.item(), loss.item(), rtol=1e-6)
+    np.testing.assert_allclose(s2.cpu().numpy()[:5], stats.cpu().numpy()[:5], rtol=1e-5)
+    ref_l, _, dx, dy = O.mk_mmd_grad(x.astype(np.float64), y.astype(np.float64))
+    assert np.isclose(loss.item(), ref_l, rtol=1e-3)
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE config 2)
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+def test_full_size_properties(mode):
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    N, d = 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(1013)
+    x = torch.randn(N, d, device="cuda", generator=g)
+    y = torch.randn(N, d, device="cuda", generator=g) * 1.25 + 0.1
+    xt = x.clone().requires_grad_(True)
+    yt = y.clone().requires_grad_(True)
+    l = edrl_b200.MK_MMD(xt, yt, precision=name)
+    l.backward()
+    lv = l.item()
+    assert np.isfinite(lv) and lv > 0
+    # symmetry in the arguments
+    assert np.isclose(edrl_b200.MK_MMD(y, x, precision=name).item(), lv, rtol=ltol)
+    # scale covariance: the bandwidth is data derived, so (aX, aY) gives the same loss
+    assert np.isclose(edrl_b200.MK_MMD(3.0 * x, 3.0 * y, precision=name).item(), lv, rtol=ltol * 3)
+    # permutation invariance within each set
+    px = x[torch.randperm(N, device="cuda")]
+    assert np.isclose(edrl_b200.MK_MMD(px, y, precision=name).item(), lv, rtol=ltol)
+    # translation invariance => gradients sum to zero over all rows
+    gsum = (xt.grad.sum(0) + yt.grad.sum(0)).abs().max().item()
+    gmax = max(xt.grad.abs().max().item(), yt.grad.abs().max().item())
+    assert gsum <= gtol * gmax * np.sqrt(2 * N), (gsum, gmax)
+    # directional derivative against a forward difference (3xTF32 forward for the difference quotient)
+    v = xt.grad / xt.grad.norm()
+    t = 0.5
+    lp = edrl_b200.MK_MMD(x + t * v, y, precision="3xtf32").item()
+    lm = edrl_b200.MK_MMD(x - t * v, y, precision="3xtf32").item()
+    fd = (lp - lm) / (2 * t)
+    an = (xt.grad * v).sum().item()
+    assert np.isclose(fd, an, rtol=5e-2), (fd, an)
+    # against the strided-subsample oracle: compare with a smaller exact problem embedded? (not possible) ->
+    # instead cross-check the two precision modes against each other
+    l3 = edrl_b200.MK_MMD(x, y, precision="3xtf32").item()
+    assert np.isclose(lv, l3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+def test_midsize_vs_oracle(mode):
+    """N=2048/side, d=512 -- the largest size the fp64 numpy oracle finishes in seconds."""
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    x, y = mmd_inputs(1011, 2048, 2048, 512, 0.1, 1.25)
+    x, y = x.numpy(), y.numpy()
+    xt = dev(x).requires_grad_(True)
+    yt = dev(y).requires_grad_(True)
+    l = edrl_b200.MK_MMD(xt, yt, precision=name)
+    l.backward()
+    ref_l, _, dx, dy = O.mk_mmd_grad(x, y)
+    assert np.isclose(l.item(), ref_l, rtol=ltol, atol=1e-6), (l.item(), ref_l)
+    gmax = max(np.abs(dx).max(), np.abs(dy).max())
+    assert np.abs(xt.grad.cpu().numpy() - dx).max() <= gtol * gmax
+    assert np.abs(yt.grad.cpu().numpy() - dy).max() <= gtol * gmax
