@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -388,7 +388,10 @@ def run_ours(args, rank, local_rank, world):
         dist.barrier()
 
     if rank == 0:
-        cpu_v, cores, sample, _ = cpu_port_sample(N, d, wl["seed"])
+        if args.no_cpu_baseline:
+            cpu_v, cores, sample = None, 0, "skipped (--no-cpu-baseline, profiling run)"
+        else:
+            cpu_v, cores, sample, _ = cpu_port_sample(N, d, wl["seed"])
         extras = {} if (args.no_extras or sharded) else essence_point_extras(peaks)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -423,6 +426,7 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = dist_env()

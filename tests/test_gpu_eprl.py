@@ -128,7 +128,7 @@ def test_module_eval_branch_matches_reference_golden(key, ge):
     model = edrl_b200.EPRL(xd, z_dim=zd, sample_num=s, num_classes=2, seed=1, batch_size=b).cuda()
     with torch.no_grad():
         model.proxies.copy_(dev(ge[key + "_proxies"]))
-        model.alpha.copy_(dev(ge[key + "_eval_alpha"]))
+        model.alpha.copy_(dev(ge[key + "_eval_alpha"]).reshape(()))
         mlp = model.mlp_2d if t == 144 else model.mlp_3d
         mlp[1].weight.copy_(dev(ge[key + "_eval_mlp_w"]))
         mlp[1].bias.copy_(dev(ge[key + "_eval_mlp_b"]))

@@ -1,0 +1,11 @@
+#!/bin/bash
+# ncu evidence for the bench command (B200_PROFILING.md recipe): plain run first, then the launch list,
+# then one --set full capture of the two MMD kernels.
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_kernel" -s 6 -c 2 -o gpurun_out/prof_mmd -f $CMD > gpurun_out/ncu_full.log 2>&1
+echo "full capture rc=$?"
