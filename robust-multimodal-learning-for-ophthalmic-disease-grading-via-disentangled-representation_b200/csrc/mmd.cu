@@ -48,7 +48,7 @@ struct Layout {
 static Layout make_layout(int n_s, int n_t, int d, int flags) {
   Layout L;
   L.n = n_s + n_t;
-  L.n_pad = (int)align_up((size_t)L.n, 128);
+  L.n_pad = (int)align_up((size_t)L.n, 256);   // 256: the pair forward works on 256 x 256 tiles
   L.d_pad = (int)align_up((size_t)d, 64);   // 64: the pair kernels stage two 32-column chunks at a time
   L.split3 = (flags & EDRL_MMD_3XTF32) != 0;
   size_t o = 0;
@@ -205,13 +205,16 @@ __device__ __forceinline__ void fill_generic_coefs(float *s_negc, float *s_w, fl
 }
 
 __device__ __forceinline__ void decode_tile(long long t, int nb, int &I, int &J) {
-  // upper-triangular tiles in row-major order: row I holds nb - I tiles, offset(I) = I nb - I (I-1) / 2
-  const double b = 2.0 * nb + 1.0;
-  int i = (int)floor((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+  // upper-triangular tiles in row-major order: row I holds nb - I tiles, offset(I) = I nb - I (I-1) / 2.
+  // fp32 estimate + exact integer correction (no fp64 in the per-tile path: sixteen epilogue warps decoding
+  // with a double-precision sqrt showed up as FP64-pipe stalls in the profile).
+  const float b = 2.0f * (float)nb + 1.0f;
+  const float disc = fmaxf(b * b - 8.0f * (float)t, 0.0f);
+  int i = (int)((b - sqrtf(disc)) * 0.5f);
   if (i < 0) i = 0;
   if (i > nb - 1) i = nb - 1;
   while ((long long)i * nb - (long long)i * (i - 1) / 2 > t) --i;
-  while ((long long)(i + 1) * nb - (long long)(i + 1) * i / 2 <= t) ++i;
+  while (i < nb - 1 && (long long)(i + 1) * nb - (long long)(i + 1) * i / 2 <= t) ++i;
   I = i;
   J = i + (int)(t - ((long long)i * nb - (long long)i * (i - 1) / 2));
 }
@@ -504,6 +507,234 @@ mmd_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
+  }
+}
+
+
+// ----------------------------------------------------------------------------- K2p: CTA-pair forward (TF32)
+// Persistent 2-CTA clusters; each pair owns 256 x 256 upper-triangular tiles of the Gram matrix:
+// tcgen05 cta_group::2, M = 256 (128 rows of Z_I per CTA), N = 256 (128 rows of Z_J per CTA), K = d.
+// Per 128 x 256 half-tile a CTA ingests 32 KiB per 32 columns of d (its rows of Z_I + half of Z_J) -- half of what
+// the 128 x 128 single-CTA kernel moves per output element; both are bound by the L2 -> SM ingest rate.
+constexpr int F2_TILE = 256;
+constexpr int F2_STAGE = 2 * TILE_BYTES;          // 128 rows of Z_I + 128 rows of Z_J, 32 columns each
+constexpr int F2_STAGES = 6;
+constexpr int F2_CTRL_BYTES = 6144;
+constexpr int F2_EPI_WARPS = 16;              // 4 per TMEM lane group, 64 accumulator columns each
+constexpr int F2_EPI_THREADS = F2_EPI_WARPS * 32;
+constexpr int F2_THREADS = 64 + F2_EPI_THREADS;
+constexpr int F2_SMEM_BYTES = F2_STAGES * F2_STAGE + F2_CTRL_BYTES;
+
+struct Fwd2Ctrl {
+  uint64_t full[8];              // leader CTA only
+  uint64_t empty[8];             // per CTA (multicast commit)
+  uint64_t tmem_full[2];         // per CTA (multicast commit)
+  uint64_t tmem_empty[2];        // leader, 16 arrivals
+  uint32_t tmem_base;
+  uint32_t pad;
+  float2 colinfo[2][F2_TILE];    // (r_j, a_j) of the current J block, per accumulator stage
+  float negc[MAX_KERNELS];
+  float w[MAX_KERNELS];
+  double red[F2_EPI_WARPS][2];
+};
+static_assert(sizeof(Fwd2Ctrl) <= F2_CTRL_BYTES, "Fwd2Ctrl does not fit its smem slot");
+static_assert(F2_SMEM_BYTES <= 232448, "smem budget");
+
+template <bool FAST>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F2_THREADS, 1)
+mmd_fwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z, const FwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Fwd2Ctrl *ctl = reinterpret_cast<Fwd2Ctrl *>(smem + F2_STAGES * F2_STAGE);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int nb2 = p.n_pad / F2_TILE;
+  const long long tiles_total = (long long)nb2 * (nb2 + 1) / 2;
+  const long long q_total = (tiles_total - p.tile_rank + p.tile_world - 1) / p.tile_world;
+  const int kchunks = p.kchunks;
+
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F2_STAGES; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->tmem_full[s], 1);
+      mbar_init(&ctl->tmem_empty[s], 2 * F2_EPI_WARPS);
+    }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&ctl->tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_z);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, warp-converged issue) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t full0 = mapa_u32(smem_u32(&ctl->full[0]), 0);
+    for (long long q = pair; q < q_total; q += npairs) {
+      int I, J;
+      decode_tile(p.tile_rank + p.tile_world * q, nb2, I, J);
+      const int irow = I * F2_TILE + (int)rank * 128;
+      const int jrow = J * F2_TILE + (int)rank * 128;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&ctl->empty[s], ph ^ 1);
+        mbar_expect_tx_elect(&ctl->full[s], 2 * F2_STAGE, leader ? 1u : 0u);
+        uint8_t *st = smem + s * F2_STAGE;
+        const uint32_t bar = full0 + 8u * (uint32_t)s;
+        tma_load_2d_pair_elect(st, &tm_z, bar, kc * BK, irow);
+        tma_load_2d_pair_elect(st + TILE_BYTES, &tm_z, bar, kc * BK, jrow);
+        if (++s == F2_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, warp-converged issue) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_tf32(256, F2_TILE);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      const uint32_t ring_addr = smem_u32(smem);
+      for (long long q = pair; q < q_total; q += npairs, ++it) {
+        const int as = it & 1;
+        const uint32_t u = (uint32_t)(it >> 1);
+        mbar_wait_cluster(&ctl->tmem_empty[as], (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * F2_TILE;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&ctl->full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = ring_addr + s * F2_STAGE;
+          const uint64_t a_d = make_kmajor_sw128_desc(sa);
+          const uint64_t b_d = make_kmajor_sw128_desc(sa + TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+            mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+          }
+          mma_commit_pair_elect(&ctl->empty[s]);
+          if (++s == F2_STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        mma_commit_pair_elect(&ctl->tmem_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): thread = one row, 4 warps per lane group x 64 columns ==========
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int ch = ew >> 2;                  // column quarter (64 columns)
+    const int et = ew * 32 + lane;
+    const int row = lg * 32 + lane;
+
+    const double sum_r = p.acc[2];
+    const float sigma0 = (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num);
+    float sig_last = sigma0;
+    for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
+    const float negc_last = -LOG2E / sig_last;
+    if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
+    const uint32_t tmem_empty0 = mapa_u32(smem_u32(&ctl->tmem_empty[0]), 0);
+
+    double accM = 0.0, accD = 0.0;
+    int it = 0;
+    for (long long q = pair; q < q_total; q += npairs, ++it) {
+      int I, J;
+      decode_tile(p.tile_rank + p.tile_world * q, nb2, I, J);
+      const int as = it & 1;
+      const uint32_t u = (uint32_t)(it >> 1);
+      if (et < F2_TILE) {
+        const int gj = J * F2_TILE + et;
+        ctl->colinfo[as][et] = make_float2((float)p.racc[gj], p.a[gj]);
+      }
+      const int gi = I * F2_TILE + (int)rank * 128 + row;
+      const float ri = (float)p.racc[gi];
+      const float ai = p.a[gi];
+      named_barrier_sync(1, F2_EPI_THREADS);
+      mbar_wait(&ctl->tmem_full[as], u & 1);
+      tc_fence_after();
+      float tM = 0.f, tD = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = ch * 64 + c * 32;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(as * F2_TILE + col0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 ci = ctl->colinfo[as][col0 + j];
+          float L = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
+          L = fmaxf(L, 0.f);
+          float K, Q;
+          kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+          tM = fmaf(ci.y, K, tM);
+          tD = fmaf(ci.y * L, Q, tD);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty0 + 8u * (uint32_t)as);
+      const float wgt = (I == J) ? ai : 2.f * ai;
+      accM += (double)(wgt * tM);
+      accD += (double)(wgt * tD);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      accM += __shfl_xor_sync(0xffffffffu, accM, o);
+      accD += __shfl_xor_sync(0xffffffffu, accD, o);
+    }
+    if (lane == 0) {
+      ctl->red[ew][0] = accM;
+      ctl->red[ew][1] = accD;
+    }
+    named_barrier_sync(1, F2_EPI_THREADS);
+    if (et == 0) {
+      double m = 0.0, dd = 0.0;
+#pragma unroll
+      for (int k = 0; k < F2_EPI_WARPS; ++k) {
+        m += ctl->red[k][0];
+        dd += ctl->red[k][1];
+      }
+      atomicAdd(p.acc + 0, m);
+      atomicAdd(p.acc + 1, dd);
+      __threadfence();
+      const unsigned t = atomicAdd(p.ticket, 1u);
+      if (t == gridDim.x - 1) {
+        __threadfence();
+        const double M = atomicAdd(p.acc + 0, 0.0);
+        const double Ds = atomicAdd(p.acc + 1, 0.0);
+        if (p.partial) {
+          p.partial[0] = M;
+          p.partial[1] = Ds;
+        }
+        if (p.tile_world == 1) write_final_stats(M, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 
@@ -1364,6 +1595,24 @@ static int forward_impl(int mode, const float *X, const float *Y, int n_s, int n
   if (sms <= 0) sms = 148;
   int grid = (int)((q_total < sms) ? (q_total > 0 ? q_total : 1) : sms);
   const bool fast = (mul == 2.0f && num == 5);
+  static const bool legacy = (getenv("EDRL_MMD_FWD_LEGACY") != nullptr);   // A/B switch for profiling
+  if (mode == MODE_LOSS && !L.split3 && !legacy) {
+    // TF32 loss path: persistent CTA pairs over 256 x 256 tiles
+    const int nb2 = L.n_pad / F2_TILE;
+    const long long tiles2 = (long long)nb2 * (nb2 + 1) / 2;
+    const long long q2 = (tiles2 - tile_rank + tile_world - 1) / tile_world;
+    int pairs = sms / 2;
+    if (q2 < pairs) pairs = (int)(q2 > 0 ? q2 : 1);
+    auto kern = fast ? mmd_fwd_pair_kernel<true> : mmd_fwd_pair_kernel<false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[fast ? 1 : 0]) {
+      EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
+      attr_done[fast ? 1 : 0] = true;
+    }
+    kern<<<2 * pairs, F2_THREADS, F2_SMEM_BYTES, st>>>(tm_hi, p);
+    EDRL_LAUNCHED();
+    return 0;
+  }
   if (mode == MODE_LOSS) return launch_fwd<MODE_LOSS>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
   if (mode == MODE_KMAT) return launch_fwd<MODE_KMAT>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
   return launch_fwd<MODE_GRAM>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
@@ -1483,6 +1732,10 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
     if (res == 16) {
       if (fast) return launch_bwd_pair_t<true, 16>(tm_z64, tm_zt, p, grid2, st);
       return launch_bwd_pair_t<false, 16>(tm_z64, tm_zt, p, grid2, st);
+    }
+    if (res == 12) {
+      if (fast) return launch_bwd_pair_t<true, 12>(tm_z64, tm_zt, p, grid2, st);
+      return launch_bwd_pair_t<false, 12>(tm_z64, tm_zt, p, grid2, st);
     }
     if (res == 8) {
       if (fast) return launch_bwd_pair_t<true, 8>(tm_z64, tm_zt, p, grid2, st);

@@ -1,0 +1,60 @@
+"""Row-block sharded MK_MMD over NCCL (needs >= 2 GPUs; skipped otherwise).  Each rank holds a slice,
+the loss must equal the single-device loss of the gathered problem and each rank's gradient must be
+its rows of the global gradient (numpy oracle, fp64)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpu_util import have_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not have_gpu() or torch.cuda.device_count() < 2, reason="needs >= 2 CUDA devices")]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nl, d, prec):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import edrl_b200
+    from oracle import edrl_oracle as O
+    xs, ys = [], []
+    for r in range(world):
+        g = torch.Generator().manual_seed(2000 + r)
+        xs.append(torch.randn(nl, d, generator=g, dtype=torch.float64))
+        ys.append(torch.randn(nl, d, generator=g, dtype=torch.float64) * 1.25 + 0.1)
+    x = xs[rank].float().cuda().requires_grad_(True)
+    y = ys[rank].float().cuda().requires_grad_(True)
+    loss = edrl_b200.sharded_MK_MMD(x, y, precision=prec)
+    (2.0 * loss).backward()
+    xa, ya = torch.cat(xs).numpy(), torch.cat(ys).numpy()
+    ref, _, dx, dy = O.mk_mmd_grad(xa, ya, grad_out=2.0)
+    ltol, gtol = (1e-4, 1e-4) if prec == "3xtf32" else (1e-3, 2e-3)
+    assert np.isclose(loss.item(), ref, rtol=ltol, atol=1e-6), (loss.item(), ref)
+    gmax = max(np.abs(dx).max(), np.abs(dy).max())
+    assert np.abs(x.grad.cpu().numpy() - dx[rank * nl:(rank + 1) * nl]).max() <= gtol * gmax
+    assert np.abs(y.grad.cpu().numpy() - dy[rank * nl:(rank + 1) * nl]).max() <= gtol * gmax
+    # and against the single-device kernel on the gathered problem
+    single = edrl_b200.MK_MMD(torch.tensor(xa).float().cuda(), torch.tensor(ya).float().cuda(), precision=prec)
+    assert np.isclose(single.item(), loss.item(), rtol=1e-5)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("prec", ["tf32", "3xtf32"])
+def test_sharded_mk_mmd_nccl(prec):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), 320, 96, prec), nprocs=world, join=True)

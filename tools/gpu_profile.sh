@@ -7,5 +7,5 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_kernel" -s 6 -c 2 -o gpurun_out/prof_mmd -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_pair_kernel" -s 6 -c 2 -o gpurun_out/prof_mmd_pair -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
