@@ -240,7 +240,17 @@ def essence_point_extras(peaks):
         ms = a.elapsed_time(b) / 5
         byts = R * W * 4 + R * k * 8
         out["select_topk"] = {"rows": R, "width": W, "k": k, "ms": ms, "GB/s": byts / ms / 1e6,
-                              "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"], "rows_per_s": R / ms * 1e3}
+                              "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"], "rows_per_s": R / ms * 1e3,
+                              "order": "descending (torch.topk parity)"}
+        a.record()
+        for _ in range(5):
+            edrl_b200.topk_rows(x, k, sorted=False)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        out["select_topk_unsorted"] = {"rows": R, "width": W, "k": k, "ms": ms, "GB/s": byts / ms / 1e6,
+                                       "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
+                                       "order": "selection set only (what the Essence-Point loss consumes)"}
         del x
         B, T, D, kk = 4096, 216, 768, 32
         feat = torch.randn(B, T, D, device="cuda")
@@ -259,6 +269,47 @@ def essence_point_extras(peaks):
                               "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]}
     except Exception as exc:   # extras never take the headline down
         out["error"] = repr(exc)
+    return out
+
+
+def sweep_vs_torch_gpu(prec):
+    """BASELINE configs[1]: MK_MMD fwd+bwd sweep, d=512, against the reference's torch op sequence run eagerly on
+    the SAME GPU (oracle/cpu_port.mk_mmd_fwd_bwd is device agnostic) -- plus the reference's own training shape
+    (N=64/side, d=3072).  Baseline leg only; median of a few runs, untimed warm-up."""
+    import edrl_b200
+    from oracle import cpu_port
+    out = []
+    try:
+        for (N, d) in ((64, 3072), (256, 512), (1024, 512), (4096, 512), (8192, 512)):
+            x, y = make_inputs(N, d, 1000 + int(math.log2(N)), "cuda")
+
+            def ours():
+                a = x.detach().requires_grad_(True)
+                b = y.detach().requires_grad_(True)
+                edrl_b200.MK_MMD(a, b, precision=prec).backward()
+
+            def ref():
+                cpu_port.mk_mmd_fwd_bwd(x, y)
+
+            res = {"N_per_side": N, "d": d}
+            for name, fn, reps in (("ours_ms", ours, 10), ("torch_eager_gpu_ms", ref, 3 if N >= 4096 else 10)):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(reps):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b))
+                res[name] = statistics.median(ts)
+            res["speedup"] = res["torch_eager_gpu_ms"] / res["ours_ms"]
+            out.append(res)
+            torch.cuda.empty_cache()
+    except Exception as exc:
+        out.append({"error": repr(exc)})
     return out
 
 
@@ -410,8 +461,12 @@ def run_ours(args, rank, local_rank, world):
         }
         if base:
             line["strong_scaling_base"] = base
+            line["note"] = ("N>1 runs configs[3] (fixed total work, strong scaling); the 1-GPU time of the SAME workload is "
+                            "strong_scaling_base, while `bench.py --gpus 1` runs configs[1] (N=8192, d=512) as the contract "
+                            "asks, so per-N values are comparable only against strong_scaling_base")
         if extras:
             line["essence_point"] = extras
+            line["sweep_vs_torch_gpu"] = sweep_vs_torch_gpu(prec)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -128,15 +128,17 @@ int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int 
                    float *dzbar, float *dz_pn, void *stream);
 
 /* Generic row-wise top-k (torch.topk(x, k, dim=1), fusion_net.py:236-238): the k largest of each
- * row, sorted descending, ties lowest-index-first.  x is [R, W] with row stride ld (floats).
+ * row, ties lowest-index-first.  sorted != 0: descending by value like torch.topk(sorted=True);
+ * sorted == 0: the same set in unspecified order (the warp kernel emits ascending index order; cheaper, and
+ * enough for consumers that reduce over or gather the selection, which is all the reference does with it).  x is [R, W] with row stride ld (floats).
  * vals [R,k], idx [R,k] (int32).  k > W is an error, like torch. */
-int edrl_topk_rows(const float *x, int R, int W, int ld, int k, float *vals, int32_t *idx, void *stream);
+int edrl_topk_rows(const float *x, int R, int W, int ld, int k, int sorted, float *vals, int32_t *idx, void *stream);
 
 /* Label-addressed select (fusion_net.py:227-238) without masked_select:
  *   positives of row b = att[b, y_b, :]           -> pos_val/pos_idx [B,k]
  *   negatives of row b = concat_{c != y_b} att[b,c,:] (class-major) -> neg_val/neg_idx [B,k]
  * y is int64 [B]; labels outside {0,1} are rejected by the host (proxies_dict, fusion_net.py:101). */
-int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k,
+int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k, int sorted,
                          float *pos_val, int32_t *pos_idx, float *neg_val, int32_t *neg_idx, void *stream);
 
 /* proxy_loss = mean_b exp(-mean(pos_val_b) + mean(neg_val_b))  (fusion_net.py:240-243);

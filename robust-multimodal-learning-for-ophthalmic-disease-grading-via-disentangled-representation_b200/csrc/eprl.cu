@@ -9,6 +9,7 @@
 //   K8  proxy_loss_fwd / select_loss_bwd      : loss and its scatter backward (B6/B7)
 //   K9  gather_rows_{fwd,bwd}                 : feature gather by index (north-star extension)
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/edrl_b200.h"
 #include "common.cuh"
@@ -253,6 +254,11 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 struct PlainRows {          // x [R, W], row stride ld
   const float *x;
   int W, ld;
+  struct Cursor {
+    const float *base;
+    __device__ __forceinline__ const float *at(int j) const { return base + j; }
+  };
+  __device__ __forceinline__ Cursor cursor(int r) const { return Cursor{x + (size_t)r * ld}; }
   __device__ __forceinline__ int width(int) const { return W; }
   __device__ __forceinline__ const float *seg(int r, int j, int &run) const {
     run = W - j;
@@ -263,6 +269,20 @@ struct EssenceRows {        // virtual rows over att [B,C,S]: v < B positives (c
   const float *att;
   const long long *y;
   int B, C, S;
+  // negatives are the classes != y_b in class-major order: virtual element j is physical element j below the
+  // label's block and j + S from it on -- one compare per element instead of a division
+  struct Cursor {
+    const float *base;
+    int skip_from, skip;
+    __device__ __forceinline__ const float *at(int j) const { return base + j + ((j >= skip_from) ? skip : 0); }
+  };
+  __device__ __forceinline__ Cursor cursor(int v) const {
+    const int b = (v < B) ? v : v - B;
+    const int yb = min(max((int)y[b], 0), C - 1);
+    const float *row = att + (size_t)b * C * S;
+    if (v < B) return Cursor{row + (size_t)yb * S, 0x7fffffff, 0};
+    return Cursor{row, yb * S, S};
+  }
   __device__ __forceinline__ int width(int v) const { return (v < B) ? S : (C - 1) * S; }
   // pointer to element j of virtual row v and the number of contiguous elements that follow it
   __device__ __forceinline__ const float *seg(int v, int j, int &run) const {
@@ -385,6 +405,234 @@ topk_warp_kernel(Rows rows, int R, int k, int KP, float *__restrict__ vals, int 
     const unsigned long long c = buf[t];
     vals[(size_t)r * k + t] = key2f((uint32_t)(c >> 32));
     idx[(size_t)r * k + t] = (int)(0xffffffffu - (uint32_t)(c & 0xffffffffu));
+  }
+}
+
+
+// One warp per row, the row in registers as order-preserving keys (W <= 32 E), k <= 128.
+// Select: MSD radix select, 8 bits per pass, on a warp-private 256-bin shared-memory histogram (at most 4 passes,
+// usually 3; stops as soon as the boundary bucket is taken whole).  That is ~12 instructions per element instead
+// of the ~2 x 20 of the bit-by-bit search in topk_warp_kernel.  Winners are compacted in ascending index order
+// (ties: lowest index first); SORTED additionally runs a 128-element bitonic network in registers (4 per lane,
+// 64-bit key|~index composites, shuffles for the cross-lane stages) to give torch.topk's descending order.
+template <int SIZE, int STRIDE>
+__device__ __forceinline__ void bitonic_step_reg(unsigned long long (&c)[4], int lane) {
+  if (STRIDE >= 4) {
+    const int lx = STRIDE >> 2;
+    const bool lower = (lane & lx) == 0;
+    const bool desc = (SIZE >= 128) ? true : ((lane & (SIZE >> 2)) == 0);
+    const bool keep_max = (lower == desc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, c[i], lx);
+      c[i] = keep_max ? (c[i] > o ? c[i] : o) : (c[i] < o ? c[i] : o);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((i & STRIDE) == 0) {
+        const int p = i | STRIDE;
+        bool desc;
+        if (SIZE == 2) desc = ((i & 2) == 0);
+        else if (SIZE == 4) desc = ((lane & 1) == 0);
+        else if (SIZE >= 128) desc = true;
+        else desc = ((lane & (SIZE >> 2)) == 0);
+        const unsigned long long a = c[i], b = c[p];
+        const bool swap = desc ? (a < b) : (a > b);
+        c[i] = swap ? b : a;
+        c[p] = swap ? a : b;
+      }
+    }
+  }
+}
+
+// order-preserving key with two integer ops: flip all bits of negatives, only the sign bit of the rest
+__device__ __forceinline__ uint32_t f2key_fast(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+// hist[dg] += 1 if (key >= lo && dg < nbins), as ONE predicated shared-memory reduction (no branch)
+__device__ __forceinline__ void hist_inc_if(uint32_t hist_addr, uint32_t key, uint32_t lo, uint32_t dg,
+                                            uint32_t nbins) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ge.u32 q, %1, %2;\n\t"
+      "setp.lt.and.u32 q, %3, %4, q;\n\t"
+      "@q red.shared.add.u32 [%0], 1;\n\t"
+      "}\n" ::"r"(hist_addr + (dg << 2)),
+      "r"(key), "r"(lo), "r"(dg), "r"(nbins)
+      : "memory");
+}
+
+// buf[slot] = (~index, key) if p, as one predicated store (no branch)
+__device__ __forceinline__ void st_shared_v2_if(uint32_t addr, uint32_t x, uint32_t y, bool p) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q st.shared.v2.u32 [%0], {%1, %2};\n\t"
+      "}\n" ::"r"(addr),
+      "r"(x), "r"(y), "r"((uint32_t)p)
+      : "memory");
+}
+
+// FULL: W == 32 E exactly (no bounds checks, no padding keys).
+template <int E, bool FULL, bool SORTED, class Rows>
+__global__ void __launch_bounds__(128)
+topk_warp_radix_kernel(Rows rows, int R, int k, float *__restrict__ vals, int *__restrict__ idx) {
+  __shared__ __align__(16) unsigned int s_hist[4][256];      // per warp: histogram, later 128 64-bit winners
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + wib;
+  if (r >= R) return;
+  unsigned int *hist = s_hist[wib];
+  uint2 *buf = reinterpret_cast<uint2 *>(hist);              // .x = ~index, .y = key  (little-endian key|~index)
+  const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(hist);
+  const int W = FULL ? E * 32 : rows.width(r);
+  const typename Rows::Cursor cur = rows.cursor(r);
+  uint32_t key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int j = e * 32 + lane;
+    if (FULL || j < W)
+      key[e] = max(f2key_fast(__ldg(cur.at(j))), 1u);        // 0 stays reserved for padding (only -NaN maps there)
+    else
+      key[e] = 0u;
+  }
+  // ---- range-adaptive radix select: after the loop every key > T wins and `need` keys == T (or, if `exact`,
+  //      every key >= T) win.  Digits are taken from (key - lo) over the row's own [lo, hi] key range, 8 bits per
+  //      pass from the top of that range, so the row spreads over the 256 bins whatever its exponent range is.
+  uint32_t kmin = 0xffffffffu, kmax = 1u;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    kmin = min(kmin, (FULL || key[e] != 0u) ? key[e] : 0xffffffffu);
+    kmax = max(kmax, key[e]);
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  int shift = 32 - __clz((kmax - kmin) | 1u) - 8;            // ((kmax - kmin) >> shift) < 256
+  if (shift < 0) shift = 0;
+  uint32_t lo = kmin;                                        // candidates: keys in [lo, lo + (nbins << shift))
+  uint32_t nbins = 256u;
+  int need = k;
+  bool exact = false;
+#pragma unroll 1
+  for (;;) {
+    reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e) hist_inc_if(hist_addr, key[e], lo, (key[e] - lo) >> shift, nbins);
+    __syncwarp();
+    // lane l owns bins 8 (31 - l) .. 8 (31 - l) + 7, walked from the top: lane 0 holds the 8 largest digits
+    const int base = (31 - lane) * 8;
+    const uint4 hlo = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2];
+    const uint4 hhi = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2 + 1];
+    const int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
+    const int t = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    int incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
+    const int L = __ffs(hit) - 1;                            // candidates number >= need: a lane always hits
+    int packed = 0;                                          // bin | cntb << 8 | rem << 20
+    if (lane == L) {
+      int rem = need - (incl - t);
+      int bin = 0, cntb = 0;
+      bool found = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!found) {
+          if (c[i] >= rem) {
+            bin = base + 7 - i;
+            cntb = c[i];
+            found = true;
+          } else {
+            rem -= c[i];
+          }
+        }
+      }
+      packed = bin | (cntb << 8) | (rem << 20);              // counts <= 2048 fit 12 bits
+    }
+    packed = __shfl_sync(0xffffffffu, packed, L);
+    const int bin = packed & 255, cntb = (packed >> 8) & 4095;
+    need = packed >> 20;
+    lo += (uint32_t)bin << shift;                            // the boundary bucket is [lo, lo + (1 << shift))
+    if (cntb == need) {                                      // whole boundary bucket taken: every key >= lo wins
+      exact = true;
+      break;
+    }
+    if (shift == 0) break;                                   // bucket == one key value: `need` of its duplicates win
+    nbins = (shift >= 8) ? 256u : (1u << shift);
+    shift = (shift > 8) ? shift - 8 : 0;                     // split the bucket into (up to) 256 sub-buckets
+  }
+  const uint32_t T = lo;
+  __syncwarp();
+  // ---- compaction in ascending index order (e-major, then lane): slot = number of winners before this element
+  {
+    uint4 *b4 = reinterpret_cast<uint4 *>(hist);
+    b4[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+    b4[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncwarp();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int basec = 0;
+  if (exact) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool win = key[e] >= T && (FULL || key[e] != 0u);
+      const uint32_t m = __ballot_sync(0xffffffffu, win);
+      st_shared_v2_if(hist_addr + 8u * (uint32_t)(basec + __popc(m & lt_mask)), ~(uint32_t)(e * 32 + lane), key[e], win);
+      basec += __popc(m);
+    }
+  } else {
+    int need_eq = need;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t kv = key[e];
+      const bool eq = (kv == T);
+      const uint32_t m_eq = __ballot_sync(0xffffffffu, eq);
+      const bool win = (kv > T) || (eq && __popc(m_eq & lt_mask) < need_eq);
+      const uint32_t m = __ballot_sync(0xffffffffu, win);
+      if (win) buf[basec + __popc(m & lt_mask)] = make_uint2(~(uint32_t)(e * 32 + lane), kv);
+      basec += __popc(m);
+      need_eq -= min(need_eq, __popc(m_eq));
+    }
+  }
+  __syncwarp();
+  if (SORTED) {
+    unsigned long long c4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c4[i] = reinterpret_cast<const unsigned long long *>(hist)[lane * 4 + i];
+    bitonic_step_reg<2, 1>(c4, lane);
+    bitonic_step_reg<4, 2>(c4, lane);   bitonic_step_reg<4, 1>(c4, lane);
+    bitonic_step_reg<8, 4>(c4, lane);   bitonic_step_reg<8, 2>(c4, lane);   bitonic_step_reg<8, 1>(c4, lane);
+    bitonic_step_reg<16, 8>(c4, lane);  bitonic_step_reg<16, 4>(c4, lane);  bitonic_step_reg<16, 2>(c4, lane);
+    bitonic_step_reg<16, 1>(c4, lane);
+    bitonic_step_reg<32, 16>(c4, lane); bitonic_step_reg<32, 8>(c4, lane);  bitonic_step_reg<32, 4>(c4, lane);
+    bitonic_step_reg<32, 2>(c4, lane);  bitonic_step_reg<32, 1>(c4, lane);
+    bitonic_step_reg<64, 32>(c4, lane); bitonic_step_reg<64, 16>(c4, lane); bitonic_step_reg<64, 8>(c4, lane);
+    bitonic_step_reg<64, 4>(c4, lane);  bitonic_step_reg<64, 2>(c4, lane);  bitonic_step_reg<64, 1>(c4, lane);
+    bitonic_step_reg<128, 64>(c4, lane); bitonic_step_reg<128, 32>(c4, lane); bitonic_step_reg<128, 16>(c4, lane);
+    bitonic_step_reg<128, 8>(c4, lane);  bitonic_step_reg<128, 4>(c4, lane);  bitonic_step_reg<128, 2>(c4, lane);
+    bitonic_step_reg<128, 1>(c4, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pos = lane * 4 + i;
+      if (pos < k) {
+        vals[(size_t)r * k + pos] = key2f((uint32_t)(c4[i] >> 32));
+        idx[(size_t)r * k + pos] = (int)~(uint32_t)(c4[i] & 0xffffffffu);
+      }
+    }
+  } else {
+    for (int t2 = lane; t2 < k; t2 += 32) {
+      const uint2 cc = buf[t2];
+      vals[(size_t)r * k + t2] = key2f(cc.y);
+      idx[(size_t)r * k + t2] = (int)~cc.x;
+    }
   }
 }
 
@@ -540,10 +788,41 @@ static int next_pow2(int v) {
   return p;
 }
 
+template <int E, class Rows>
+static void launch_radix(const Rows &rows, int R, int k, bool sorted, bool full, float *vals, int *idx,
+                         cudaStream_t st) {
+  const int grid = (R + 3) / 4;
+  if (full) {
+    if (sorted)
+      topk_warp_radix_kernel<E, true, true, Rows><<<grid, 128, 0, st>>>(rows, R, k, vals, idx);
+    else
+      topk_warp_radix_kernel<E, true, false, Rows><<<grid, 128, 0, st>>>(rows, R, k, vals, idx);
+  } else {
+    if (sorted)
+      topk_warp_radix_kernel<E, false, true, Rows><<<grid, 128, 0, st>>>(rows, R, k, vals, idx);
+    else
+      topk_warp_radix_kernel<E, false, false, Rows><<<grid, 128, 0, st>>>(rows, R, k, vals, idx);
+  }
+}
+
+// Wmax: widest row; uniform: every row has exactly Wmax elements
 template <class Rows>
-static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, int *idx, cudaStream_t st) {
+static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, int *idx, cudaStream_t st,
+                       bool sorted = true, bool uniform = true) {
   const int KP = next_pow2(k < 32 ? 32 : k);
   EDRL_CHECK_ARG(KP <= 1024, "topk: k = %d is larger than the supported 1024", k);
+  static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
+  if (Wmax <= 2048 && k <= 128 && !legacy) {
+    const bool full = uniform && (Wmax % 32 == 0);
+    if (Wmax <= 256) launch_radix<8>(rows, R, k, sorted, full && Wmax == 256, vals, idx, st);
+    else if (Wmax <= 512) launch_radix<16>(rows, R, k, sorted, full && Wmax == 512, vals, idx, st);
+    else if (Wmax <= 800) launch_radix<25>(rows, R, k, sorted, full && Wmax == 800, vals, idx, st);
+    else if (Wmax <= 1024) launch_radix<32>(rows, R, k, sorted, full && Wmax == 1024, vals, idx, st);
+    else if (Wmax <= 1600) launch_radix<50>(rows, R, k, sorted, full && Wmax == 1600, vals, idx, st);
+    else launch_radix<64>(rows, R, k, sorted, full && Wmax == 2048, vals, idx, st);
+    EDRL_LAUNCHED();
+    return 0;
+  }
   if (Wmax <= 2048 && KP <= 256) {
     const size_t smem = (size_t)4 * KP * sizeof(unsigned long long);
     const int grid = (R + 3) / 4;
@@ -749,15 +1028,16 @@ int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int 
   return 0;
 }
 
-int edrl_topk_rows(const float *x, int R, int W, int ld, int k, float *vals, int32_t *idx, void *stream) {
+int edrl_topk_rows(const float *x, int R, int W, int ld, int k, int sorted, float *vals, int32_t *idx,
+                   void *stream) {
   EDRL_CHECK_ARG(x && vals && idx, "topk: null argument");
   EDRL_CHECK_ARG(R > 0 && W > 0 && ld >= W, "topk: bad shape R=%d W=%d ld=%d", R, W, ld);
   EDRL_CHECK_ARG(k >= 1 && k <= W, "selected index k out of range (k=%d, row width %d)", k, W);
   PlainRows rows{x, W, ld};
-  return launch_topk(rows, R, W, k, vals, idx, ST(stream));
+  return launch_topk(rows, R, W, k, vals, idx, ST(stream), sorted != 0);
 }
 
-int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k, float *pos_val,
+int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k, int sorted, float *pos_val,
                          int32_t *pos_idx, float *neg_val, int32_t *neg_idx, void *stream) {
   EDRL_CHECK_ARG(att && y && pos_val && pos_idx && neg_val && neg_idx, "select_topk_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && C >= 2 && S > 0, "select_topk_fwd: bad shape B=%d C=%d S=%d", B, C, S);
@@ -765,7 +1045,8 @@ int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S
   EDRL_CHECK_ARG(pos_val + (size_t)B * k == neg_val && pos_idx + (size_t)B * k == neg_idx,
                  "select_topk_fwd: pos/neg outputs must be the two halves of one [2B, k] buffer");
   EssenceRows rows{att, reinterpret_cast<const long long *>(y), B, C, S};
-  return launch_topk(rows, 2 * B, (C - 1) * S, k, pos_val, pos_idx, ST(stream));
+  return launch_topk(rows, 2 * B, (C - 1) * S > S ? (C - 1) * S : S, k, pos_val, pos_idx, ST(stream), sorted != 0,
+                     /*uniform=*/C == 2);
 }
 
 int edrl_proxy_loss_fwd(const float *pos_val, const float *neg_val, int B, int k, float *loss, float *rowexp,

@@ -89,7 +89,7 @@ class _SelectLossFunction(torch.autograd.Function):
     (code/fusion_net.py:227-243).  Also returns the selected values / indices."""
 
     @staticmethod
-    def forward(ctx, att, y, k):
+    def forward(ctx, att, y, k, sorted_):
         lib = _lib.load()
         att = _f32c(att)
         B, C, S = att.shape
@@ -100,7 +100,8 @@ class _SelectLossFunction(torch.autograd.Function):
         idx = torch.empty(2, B, k, dtype=torch.int32, device=dev)
         loss = torch.empty((), device=dev)
         rowexp = torch.empty(B, device=dev)
-        _lib.check(lib.edrl_select_topk_fwd(att.data_ptr(), y.data_ptr(), B, C, S, k, vals[0].data_ptr(),
+        _lib.check(lib.edrl_select_topk_fwd(att.data_ptr(), y.data_ptr(), B, C, S, k, int(bool(sorted_)),
+                                            vals[0].data_ptr(),
                                             idx[0].data_ptr(), vals[1].data_ptr(), idx[1].data_ptr(), st))
         _lib.check(lib.edrl_proxy_loss_fwd(vals[0].data_ptr(), vals[1].data_ptr(), B, k, loss.data_ptr(),
                                            rowexp.data_ptr(), st))
@@ -120,7 +121,7 @@ class _SelectLossFunction(torch.autograd.Function):
         datt = torch.empty(B, C, S, device=rowexp.device)
         _lib.check(lib.edrl_select_loss_bwd(rowexp.data_ptr(), idx[0].data_ptr(), idx[1].data_ptr(), y.data_ptr(),
                                             g.data_ptr(), B, C, S, k, datt.data_ptr(), st))
-        return datt, None, None
+        return datt, None, None, None
 
 
 def essence_scores(z, mu, sigma, eps):
@@ -131,19 +132,21 @@ def essence_scores(z, mu, sigma, eps):
     return _ScoreFunction.apply(z, mu, sigma, eps)
 
 
-def essence_select_loss(att, y, k=SELF_TOPK):
-    """(proxy_loss, top values [2,B,k] (pos, neg), top indices [2,B,k])."""
+def essence_select_loss(att, y, k=SELF_TOPK, sorted=True):
+    """(proxy_loss, top values [2,B,k] (pos, neg), top indices [2,B,k]).  ``sorted=False`` returns the same
+    selection in ascending index order (the loss only averages it)."""
     _lib.require_cuda(att)
     B, C, S = att.shape
     if k > S:
         # torch.topk(att_positive, 100, dim=1) in the reference raises this RuntimeError
         raise RuntimeError("selected index k out of range")
-    return _SelectLossFunction.apply(att, y, int(k))
+    return _SelectLossFunction.apply(att, y, int(k), bool(sorted))
 
 
-def topk_rows(x, k):
+def topk_rows(x, k, sorted=True):
     """torch.topk(x, k, dim=1) on the select kernel: (values [R,k] descending, indices int32 [R,k]),
-    ties lowest-index-first.  Not differentiable (use select_gather for the gather path)."""
+    ties lowest-index-first; ``sorted=False`` gives the same set in ascending index order.
+    Not differentiable (use select_gather for the gather path)."""
     _lib.require_cuda(x)
     if x.dim() != 2:
         raise RuntimeError("topk_rows expects a 2-D tensor")
@@ -160,8 +163,8 @@ def topk_rows(x, k):
     vals = torch.empty(R, k, device=x.device)
     idx = torch.empty(R, k, dtype=torch.int32, device=x.device)
     if R:
-        _lib.check(lib.edrl_topk_rows(x.data_ptr(), R, W, x.stride(0), k, vals.data_ptr(), idx.data_ptr(), st),
-                   RuntimeError)
+        _lib.check(lib.edrl_topk_rows(x.data_ptr(), R, W, x.stride(0), k, int(bool(sorted)), vals.data_ptr(),
+                                      idx.data_ptr(), st), RuntimeError)
     return vals, idx
 
 
@@ -199,10 +202,10 @@ def gather_rows(features, idx):
     return _GatherRowsFunction.apply(features, idx)
 
 
-def select_gather(features, scores, k):
+def select_gather(features, scores, k, sorted=True):
     """North-star extension (no reference code): top-k over scores [B,T], gather features [B,T,D].
     Returns (gathered [B,k,D], values [B,k], indices int32 [B,k])."""
-    vals, idx = topk_rows(scores, k)
+    vals, idx = topk_rows(scores, k, sorted)
     return gather_rows(features, idx), vals, idx
 
 
@@ -319,7 +322,7 @@ class EPRL(nn.Module):
                 raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
                                  f"[{B}], [{proxy_indices.numel()}]")
             row_labels = proxy_indices.expand(B).contiguous()
-            proxy_loss, _, _ = essence_select_loss(att, row_labels, self.self_topk)
+            proxy_loss, _, _ = essence_select_loss(att, row_labels, self.self_topk, sorted=False)
             entropy_loss = self.entropy_regularization(combined)
             return mu_proxy.repeat(B, 1, 1), sigma_proxy.repeat(B, 1, 1), proxy_loss, z, entropy_loss
 
@@ -334,7 +337,7 @@ class EPRL(nn.Module):
             raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
                              f"[{B}], [{labels.numel()}]")
         att, _ = essence_scores(z, mu_proxy, sigma_proxy, eps_proxy)
-        proxy_loss, _, _ = essence_select_loss(att, labels, self.self_topk)
+        proxy_loss, _, _ = essence_select_loss(att, labels, self.self_topk, sorted=False)
         return mu_proxy.repeat(B, 1, 1), sigma_proxy.repeat(B, 1, 1), proxy_loss, z
 
     @staticmethod

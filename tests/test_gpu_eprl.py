@@ -43,6 +43,21 @@ def test_topk_rows_bit_exact(R, W, k):
     np.testing.assert_array_equal(i.cpu().numpy(), oi)
 
 
+@pytest.mark.parametrize("R,W,k", [(64, 800, 100), (9, 1600, 100), (5, 300, 17), (3, 2048, 128), (4, 8192, 100)])
+def test_topk_rows_unsorted_is_the_same_set(R, W, k):
+    import edrl_b200
+    g = torch.Generator().manual_seed(R + W)
+    x = torch.randn(R, W, generator=g)
+    x[0, :50] = 0.25                                             # ties straddling the threshold are possible
+    v, i = edrl_b200.topk_rows(x.cuda(), k, sorted=False)
+    sv, si = edrl_b200.topk_rows(x.cuda(), k, sorted=True)
+    order = torch.argsort(i.long(), dim=1)
+    order_s = torch.argsort(si.long(), dim=1)
+    assert torch.equal(torch.gather(i, 1, order), torch.gather(si, 1, order_s))
+    assert torch.equal(torch.gather(v, 1, order), torch.gather(sv, 1, order_s))
+    assert torch.equal(torch.gather(x.cuda(), 1, i.long()), v)
+
+
 @pytest.mark.parametrize("W", [800, 5000])
 def test_topk_ties_and_specials(W):
     import edrl_b200
