@@ -56,3 +56,30 @@ def rowblock_fwd_bwd(z: torch.Tensor, ns: int, r0: int, m: int, kernel_mul: floa
     part = (a[r0:r0 + m, None] * a[None, :] * kblk).sum()
     part.backward()
     return part.detach(), zi.grad
+
+
+def eprl_train_fwd_bwd(z, proxies, eps, y, z_dim, k=100):
+    """The reference's EPRL train-branch arithmetic after the encoder (code/fusion_net.py:137-150, 220-243) as
+    the same torch op sequence (normalize over tokens / samples, expanded batched matmul, permute + mean,
+    masked_select split, two top-k, exp/mean), forward + backward.  Device agnostic; baseline leg only."""
+    import torch.nn.functional as F
+    z = z.detach().clone().requires_grad_(True)
+    proxies = proxies.detach().clone().requires_grad_(True)
+    b = z.shape[0]
+    mu = proxies[:, :z_dim]                                                   # :116-119
+    sigma = F.softplus(proxies[:, z_dim:])
+    z_proxy = mu.unsqueeze(1) + sigma.unsqueeze(1) * eps                      # :143-146
+    z_norm = F.normalize(z, dim=1)                                            # :149
+    zp_norm = F.normalize(z_proxy)                                            # :150
+    zp_exp = zp_norm.unsqueeze(0).expand(b, -1, -1, -1)                       # :221
+    att = torch.matmul(z_norm.unsqueeze(1), zp_exp.transpose(2, 3))           # :223
+    att = att.permute(0, 2, 1, 3).mean(dim=1)                                 # :224-225
+    mask = torch.zeros(b, att.shape[1], dtype=torch.bool, device=z.device)    # :230-231
+    mask[torch.arange(b, device=z.device), y] = True
+    pos = torch.masked_select(att, mask.unsqueeze(-1)).view(b, -1)            # :233-234
+    neg = torch.masked_select(att, ~mask.unsqueeze(-1)).view(b, -1)
+    tp, _ = torch.topk(pos, k, dim=1)                                         # :236-238
+    tn, _ = torch.topk(neg, k, dim=1)
+    loss = torch.mean(torch.exp(-tp.mean(dim=1) + tn.mean(dim=1)))            # :240-243
+    loss.backward()
+    return loss.detach(), z.grad, proxies.grad

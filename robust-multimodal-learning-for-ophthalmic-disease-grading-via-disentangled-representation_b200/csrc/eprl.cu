@@ -79,6 +79,81 @@ token_stats_bwd_kernel(const float *__restrict__ z, const float *__restrict__ co
   dz[i] = fmaf(beta, z[i], alpha);
 }
 
+
+// 128-bit variants (F % 4 == 0, 16-byte aligned z): the streams over z are the HBM traffic of Part B.
+// forward: grid (ceil(F/128), B), block (32, 8): lane -> one float4 column group, y -> token slice
+__global__ void __launch_bounds__(256)
+token_stats_fwd_v4_kernel(const float4 *__restrict__ z, int T, int F4, float4 *__restrict__ zbar,
+                          float4 *__restrict__ colsum, float4 *__restrict__ colnorm) {
+  __shared__ float4 s_sum[8][33], s_sq[8][33];
+  const int f4 = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y;
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), sq = sum;
+  if (f4 < F4) {
+    const float4 *zp = z + (size_t)b * T * F4 + f4;
+#pragma unroll 4
+    for (int t = threadIdx.y; t < T; t += 8) {
+      const float4 v = __ldg(zp + (size_t)t * F4);
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      sq.x = fmaf(v.x, v.x, sq.x); sq.y = fmaf(v.y, v.y, sq.y); sq.z = fmaf(v.z, v.z, sq.z); sq.w = fmaf(v.w, v.w, sq.w);
+    }
+  }
+  s_sum[threadIdx.y][threadIdx.x] = sum;
+  s_sq[threadIdx.y][threadIdx.x] = sq;
+  __syncthreads();
+  if (threadIdx.y == 0 && f4 < F4) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 a = s_sum[k][threadIdx.x], q = s_sq[k][threadIdx.x];
+      sum.x += a.x; sum.y += a.y; sum.z += a.z; sum.w += a.w;
+      sq.x += q.x; sq.y += q.y; sq.z += q.z; sq.w += q.w;
+    }
+    const float4 nrm = make_float4(sqrtf(sq.x), sqrtf(sq.y), sqrtf(sq.z), sqrtf(sq.w));
+    const float ft = (float)T;
+    const size_t o = (size_t)b * F4 + f4;
+    colsum[o] = sum;
+    colnorm[o] = nrm;
+    zbar[o] = make_float4(sum.x / (ft * fmaxf(nrm.x, NORM_EPS)), sum.y / (ft * fmaxf(nrm.y, NORM_EPS)),
+                          sum.z / (ft * fmaxf(nrm.z, NORM_EPS)), sum.w / (ft * fmaxf(nrm.w, NORM_EPS)));
+  }
+}
+
+__device__ __forceinline__ void token_bwd_coefs(float nrm, float g, float s, float ft, float &alpha, float &beta) {
+  const float m = fmaxf(nrm, NORM_EPS);
+  alpha = g / (ft * m);
+  beta = (nrm > NORM_EPS) ? (-g * s / (ft * m * m * nrm)) : 0.f;
+}
+
+// backward: grid (ceil(T/TCH), B), block 256 = (F4 columns) x (256/F4 token rows); coefficients once per thread
+constexpr int TSB_TCH = 32;     // tokens per block
+__global__ void __launch_bounds__(256)
+token_stats_bwd_v4_kernel(const float4 *__restrict__ z, const float4 *__restrict__ colsum,
+                          const float4 *__restrict__ colnorm, const float4 *__restrict__ dzbar, int T, int F4,
+                          float4 *__restrict__ dz) {
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TSB_TCH;
+  const int t1 = min(t0 + TSB_TCH, T);
+  const int rows_per_iter = 256 / F4;            // F4 divides 256 (host checks)
+  const int f4 = threadIdx.x % F4;
+  const int ty = threadIdx.x / F4;
+  const size_t o = (size_t)b * F4 + f4;
+  const float4 nrm = __ldg(colnorm + o), g = __ldg(dzbar + o), cs = __ldg(colsum + o);
+  const float ft = (float)T;
+  float4 al, be;
+  token_bwd_coefs(nrm.x, g.x, cs.x, ft, al.x, be.x);
+  token_bwd_coefs(nrm.y, g.y, cs.y, ft, al.y, be.y);
+  token_bwd_coefs(nrm.z, g.z, cs.z, ft, al.z, be.z);
+  token_bwd_coefs(nrm.w, g.w, cs.w, ft, al.w, be.w);
+  const float4 *zp = z + (size_t)b * T * F4 + f4;
+  float4 *dp = dz + (size_t)b * T * F4 + f4;
+#pragma unroll 4
+  for (int t = t0 + ty; t < t1; t += rows_per_iter) {
+    const float4 v = __ldg(zp + (size_t)t * F4);
+    dp[(size_t)t * F4] = make_float4(fmaf(be.x, v.x, al.x), fmaf(be.y, v.y, al.y), fmaf(be.z, v.z, al.z),
+                                     fmaf(be.w, v.w, al.w));
+  }
+}
+
 // zmean[b,t] = mean_f z[b,t,f] / max(colnorm[b,f], eps); one warp per (b,t)
 __global__ void __launch_bounds__(256)
 token_featmean_kernel(const float *__restrict__ z, const float *__restrict__ colnorm, int B, int T, int F,
@@ -238,6 +313,79 @@ static int sgemm(const float *A, long long sam, long long sak, const float *B, l
   sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, M, N, K);
   EDRL_LAUNCHED();
   return 0;
+}
+
+
+// ----------------------------------------------------------------------------- K6 score kernels (skinny shapes)
+// The score contraction is [B, F] x [F, R] with B ~ 4-64, F = 256, R = C S = 1600: far too skinny for 64 x 64 tiles
+// (25 blocks forward; the dzbar product ran in 4 blocks and took 409 us).  One warp per proxy row r instead.
+// att[b, r] = sum_f zbar[b, f] z_pn[r, f]
+__global__ void __launch_bounds__(256)
+score_fwd_kernel(const float *__restrict__ zbar, const float *__restrict__ z_pn, int B, int R, int F,
+                 float *__restrict__ att) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float *pr = z_pn + (size_t)r * F;
+  for (int b = 0; b < B; ++b) {
+    const float *zb = zbar + (size_t)b * F;
+    float acc = 0.f;
+    for (int f = lane; f < F; f += 32) acc = fmaf(__ldg(zb + f), __ldg(pr + f), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) att[(size_t)b * R + r] = acc;
+  }
+}
+// dzbar[b, f] = sum_r datt[b, r] z_pn[r, f]; grid (ceil(F/32), B), block (32, 8)
+__global__ void __launch_bounds__(256)
+score_bwd_dzbar_kernel(const float *__restrict__ datt, const float *__restrict__ z_pn, int R, int F,
+                       float *__restrict__ dzbar) {
+  __shared__ float s_acc[8][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y;
+  float acc = 0.f;
+  if (f < F) {
+    const float *dr = datt + (size_t)b * R;
+    for (int r = threadIdx.y; r < R; r += 8) {
+      const float dv = __ldg(dr + r);
+      if (dv != 0.f) acc = fmaf(dv, __ldg(z_pn + (size_t)r * F + f), acc);   // datt is zero off the selection
+    }
+  }
+  s_acc[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc += s_acc[k][threadIdx.x];
+    dzbar[(size_t)b * F + f] = acc;
+  }
+}
+// dz_pn[r, f] = sum_b datt[b, r] zbar[b, f]; one warp per r
+__global__ void __launch_bounds__(256)
+score_bwd_dzpn_kernel(const float *__restrict__ datt, const float *__restrict__ zbar, int B, int R, int F,
+                      float *__restrict__ dz_pn) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  for (int f0 = 0; f0 < F; f0 += 256) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float dv = __ldg(datt + (size_t)b * R + r);
+      if (dv != 0.f) {
+        const float *zb = zbar + (size_t)b * F + f0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int f = i * 32 + lane;
+          if (f0 + f < F) acc[i] = fmaf(dv, __ldg(zb + f), acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f0 + i * 32 + lane;
+      if (f < F) dz_pn[(size_t)r * F + f] = acc[i];
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------- K7 top-k
@@ -963,8 +1111,18 @@ int edrl_token_stats_fwd(const float *z, int B, int T, int F, float *zbar, float
                          void *stream) {
   EDRL_CHECK_ARG(z && zbar && colsum && colnorm, "token_stats_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0 && B <= 65535, "token_stats_fwd: bad shape B=%d T=%d F=%d", B, T, F);
-  dim3 grid((F + 31) / 32, B), block(32, 8);
-  token_stats_fwd_kernel<<<grid, block, 0, ST(stream)>>>(z, T, F, zbar, colsum, colnorm);
+  const bool v4 = (F % 4 == 0) && ((((uintptr_t)z | (uintptr_t)zbar | (uintptr_t)colsum | (uintptr_t)colnorm) & 15) == 0);
+  if (v4) {
+    const int F4 = F / 4;
+    dim3 grid((F4 + 31) / 32, B), block(32, 8);
+    token_stats_fwd_v4_kernel<<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float4 *>(z), T, F4,
+                                                             reinterpret_cast<float4 *>(zbar),
+                                                             reinterpret_cast<float4 *>(colsum),
+                                                             reinterpret_cast<float4 *>(colnorm));
+  } else {
+    dim3 grid((F + 31) / 32, B), block(32, 8);
+    token_stats_fwd_kernel<<<grid, block, 0, ST(stream)>>>(z, T, F, zbar, colsum, colnorm);
+  }
   EDRL_LAUNCHED();
   return 0;
 }
@@ -973,9 +1131,19 @@ int edrl_token_stats_bwd(const float *z, const float *colsum, const float *colno
                          int F, float *dz, void *stream) {
   EDRL_CHECK_ARG(z && colsum && colnorm && dzbar && dz, "token_stats_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0, "token_stats_bwd: bad shape");
-  const size_t total = (size_t)B * T * F;
-  token_stats_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(z, colsum, colnorm, dzbar, T, F,
-                                                                                  total, dz);
+  const bool v4 = (F % 4 == 0) && (256 % (F / 4) == 0) && B <= 65535 &&
+                  ((((uintptr_t)z | (uintptr_t)dz | (uintptr_t)colsum | (uintptr_t)colnorm | (uintptr_t)dzbar) & 15) == 0);
+  if (v4) {
+    dim3 grid((T + TSB_TCH - 1) / TSB_TCH, B);
+    token_stats_bwd_v4_kernel<<<grid, 256, 0, ST(stream)>>>(
+        reinterpret_cast<const float4 *>(z), reinterpret_cast<const float4 *>(colsum),
+        reinterpret_cast<const float4 *>(colnorm), reinterpret_cast<const float4 *>(dzbar), T, F / 4,
+        reinterpret_cast<float4 *>(dz));
+  } else {
+    const size_t total = (size_t)B * T * F;
+    token_stats_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(z, colsum, colnorm, dzbar, T, F,
+                                                                                    total, dz);
+  }
   EDRL_LAUNCHED();
   return 0;
 }
@@ -1012,18 +1180,29 @@ int edrl_score_fwd(const float *zbar, const float *z_pn, int B, int R, int F, fl
   EDRL_CHECK_ARG(zbar && z_pn && att, "score_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_fwd: bad shape");
   // att[b, r] = sum_f zbar[b, f] z_pn[r, f]
-  return sgemm(zbar, F, 1, z_pn, 1, F, att, B, R, F, ST(stream));
+  if (B > 256) return sgemm(zbar, F, 1, z_pn, 1, F, att, B, R, F, ST(stream));     // wide batches: tiled GEMM
+  score_fwd_kernel<<<(R + 7) / 8, 256, 0, ST(stream)>>>(zbar, z_pn, B, R, F, att);
+  EDRL_LAUNCHED();
+  return 0;
 }
 
 int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int B, int R, int F, float *dzbar,
                    float *dz_pn, void *stream) {
   EDRL_CHECK_ARG(datt && zbar && z_pn, "score_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_bwd: bad shape");
+  EDRL_CHECK_ARG(B <= 65535, "score_bwd: batch too large");
   if (dzbar) {   // dzbar[b, f] = sum_r datt[b, r] z_pn[r, f]
-    if (int rc = sgemm(datt, R, 1, z_pn, F, 1, dzbar, B, F, R, ST(stream))) return rc;
+    dim3 grid((F + 31) / 32, B), block(32, 8);
+    score_bwd_dzbar_kernel<<<grid, block, 0, ST(stream)>>>(datt, z_pn, R, F, dzbar);
+    EDRL_LAUNCHED();
   }
   if (dz_pn) {   // dz_pn[r, f] = sum_b datt[b, r] zbar[b, f]
-    if (int rc = sgemm(datt, 1, R, zbar, F, 1, dz_pn, R, F, B, ST(stream))) return rc;
+    if (B > 256) {
+      if (int rc = sgemm(datt, 1, R, zbar, F, 1, dz_pn, R, F, B, ST(stream))) return rc;
+    } else {
+      score_bwd_dzpn_kernel<<<(R + 7) / 8, 256, 0, ST(stream)>>>(datt, zbar, B, R, F, dz_pn);
+      EDRL_LAUNCHED();
+    }
   }
   return 0;
 }

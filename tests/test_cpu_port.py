@@ -27,3 +27,20 @@ def test_cpu_port_rowblocks_sum_to_signed_mean():
         assert g.shape == (min(30, z.shape[0] - r0), z.shape[1])
     _, m, _, _ = O.mk_mmd_grad(x.numpy(), y.numpy())
     assert np.isclose(tot, m, rtol=1e-9)
+
+
+def test_cpu_port_eprl_matches_oracle():
+    rng = np.random.default_rng(4)
+    b, t, f, s = 5, 12, 16, 130
+    z = rng.standard_normal((b, t, f))
+    prox = rng.standard_normal((2, 2 * f)) * 0.3
+    eps = rng.standard_normal((2, s, f))
+    y = np.array([0, 1, 1, 0, 1])
+    loss, dz, dprox = cpu_port.eprl_train_fwd_bwd(torch.tensor(z), torch.tensor(prox), torch.tensor(eps),
+                                                  torch.tensor(y), f)
+    sp = np.log1p(np.exp(-np.abs(prox[:, f:]))) + np.maximum(prox[:, f:], 0)
+    bw = O.eprl_train_backward(z, prox[:, :f], sp, eps, y, k=100)
+    assert np.isclose(loss.item(), bw["loss"], rtol=1e-10)
+    np.testing.assert_allclose(dz.numpy(), bw["dz"], rtol=1e-7, atol=1e-13)
+    sig = 1.0 / (1.0 + np.exp(-prox[:, f:]))
+    np.testing.assert_allclose(dprox.numpy(), np.concatenate([bw["dmu"], bw["dsigma"] * sig], 1), rtol=1e-7, atol=1e-13)
