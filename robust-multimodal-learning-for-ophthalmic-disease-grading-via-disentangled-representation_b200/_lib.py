@@ -30,6 +30,11 @@ PROTOTYPES = {
                                   c_void_p]),
     "edrl_mmd_backward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "edrl_mmd_forward_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
+    "edrl_mmd_apply_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                    c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "edrl_mmd_kernel_matrix": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                        c_void_p, c_size_t, c_void_p]),
     "edrl_token_stats_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

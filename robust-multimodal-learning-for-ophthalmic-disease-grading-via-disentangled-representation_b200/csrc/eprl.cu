@@ -985,12 +985,9 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   } else {
     const size_t smem = (size_t)KP * sizeof(unsigned long long);
     // ~40 KiB of static shared memory + up to 8 KiB of sort staging: opt in above the 48 KiB default
-    static bool attr_done = false;
-    if (!attr_done) {
-      EDRL_CUDA_OK(cudaFuncSetAttribute(topk_block_kernel<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // per launch (cheap): the attribute is per device, a process may drive several
+  EDRL_CUDA_OK(cudaFuncSetAttribute(topk_block_kernel<Rows>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         1024 * (int)sizeof(unsigned long long)));
-      attr_done = true;
-    }
     topk_block_kernel<Rows><<<R, BLK_T, smem, st>>>(rows, R, k, KP, vals, idx);
   }
   EDRL_LAUNCHED();

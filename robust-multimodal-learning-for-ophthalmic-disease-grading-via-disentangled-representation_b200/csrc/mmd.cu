@@ -789,6 +789,13 @@ struct BwdParams {
   const float *stats;
   const float *grad_out;
   float *dz;                       // [row_count, d]
+  // fused forward + gradient pass (mmd_bwd_pair_kernel<.., FUSED = true>)
+  double *acc;                     // [0] M, [1] sum a a L Q, [2] sum r (from prep)
+  unsigned *ticket;
+  double *partial;                 // optional: partial sums out (sharded evaluation)
+  float *loss, *stats_out;         // written by the last CTA when finalize != 0
+  int n_t, finalize;
+  int row_begin2, row_count2;      // optional second row range (a rank's target rows); output rows follow range 1
 };
 
 // ring order (producer and MMA issuer walk the same sequence):
@@ -1162,12 +1169,17 @@ struct Bwd2Ctrl {
   float2 colinfo[2][BN];          // (r_j, a_j) per S stage; re-used for the row-sum exchange after the J loop
   float negc[MAX_KERNELS];
   float w[MAX_KERNELS];
+  double red[8][2];               // FUSED: per-warp partial block sums
 };
 static_assert(sizeof(Bwd2Ctrl) <= P2_CTRL_BYTES, "Bwd2Ctrl does not fit its smem slot");
 static_assert(Bwd2Cfg<0>::SMEM_BYTES <= 232448 && Bwd2Cfg<8>::SMEM_BYTES <= 232448 && Bwd2Cfg<16>::SMEM_BYTES <= 232448,
               "smem budget");
 
-template <bool FAST, int RES>
+// FUSED: the same pass also evaluates the forward block sums (M, D) in the epilogue and writes the
+// bandwidth-independent part of the gradient U_i = rowsum(G')_i z_i - (G' Z)_i with G' = -a_i a_j Q_ij / sigma_0 [L_raw >= 0];
+// the uniform term c of G is applied afterwards in closed form (edrl_mmd_apply_grad): sum_j c (z_i - z_j) = c n z_i
+// for centred Z.  A training step then touches every Gram tile once instead of 1.5 times (forward + backward).
+template <bool FAST, int RES, bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
 mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_zt,
                     const BwdParams p) {
@@ -1183,7 +1195,14 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int panel = blockIdx.x >> 1;
-  const int row_base = p.row_begin + panel * BM;          // first global row of the pair's 128-row panel
+  // the panels of row range 1 come first, then those of the optional range 2 (sharded: source rows, target rows)
+  const int np1 = (p.row_count + BM - 1) / BM;
+  const bool second = panel >= np1;
+  const int lpanel = second ? panel - np1 : panel;
+  const int rng_begin = second ? p.row_begin2 : p.row_begin;
+  const int rng_count = second ? p.row_count2 : p.row_count;
+  const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;   // row of dz this panel starts at
+  const int row_base = rng_begin + lpanel * BM;           // first global row of the pair's 128-row panel
   const int f0 = blockIdx.y * P2_FEATS;                   // first feature column of this pass
   const int nJ = p.nb;
   const int kchunks = p.kchunks;                          // even (d_pad is a multiple of 64)
@@ -1378,8 +1397,9 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const int j0 = jh * 64 + ch * 32;        // first of this thread's 32 columns inside the J tile
     const int gi = row_base + (int)rank * 64 + r;
 
-    const float sigma0 = p.stats[EDRL_MMD_STAT_SIGMA0];
-    const float cval = p.stats[EDRL_MMD_STAT_C];
+    const double sum_r = FUSED ? p.acc[2] : 0.0;
+    const float sigma0 = FUSED ? (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
+    const float cval = FUSED ? 0.f : p.stats[EDRL_MMD_STAT_C];
     float sig_last = sigma0;
     for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
     const float negc_last = -LOG2E / sig_last;
@@ -1390,6 +1410,11 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const float nai_sig = -ai / sigma0;
     const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
     float rowsum = 0.f;
+    // FUSED: forward block sums over this thread's row; rows outside [row_begin, row_begin + row_count) belong to
+    // another call (sharded evaluation), and only the first feature pass counts
+    const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
+    const float ai_m = count_row ? ai : 0.f;
+    double accM = 0.0, accD = 0.0;
 
     for (int J = 0; J < nJ; ++J) {
       const int b = J & 1;
@@ -1406,6 +1431,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 64 + ch * 32), v);
       tmem_ld_wait();
       float g[32];
+      float tM = 0.f, tD = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float2 ci = ctl->colinfo[b][j0 + j];
@@ -1413,11 +1439,20 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         const float L = fmaxf(Lraw, 0.f);
         float K, Q;
         kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
-        float gv = fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);   // a_j == 0 <=> padded column
+        if (FUSED) {
+          tM = fmaf(ci.y, K, tM);
+          tD = fmaf(ci.y * L, Q, tD);
+        }
+        float gv = FUSED ? (ci.y * Q) * nai_sig
+                         : fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);   // a_j == 0 <=> padded column
         gv = (Lraw >= 0.f) ? gv : 0.f;
         const float gh = to_tf32(gv);
         g[j] = gh;
         rowsum += gh;
+      }
+      if (FUSED) {
+        accM += (double)(ai_m * tM);
+        accD += (double)(ai_m * tD);
       }
       // this thread's 32 values of row r go to K-atom (j0 / 32) of the B operand, 128-byte swizzle
       uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
@@ -1431,6 +1466,41 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       if (lane == 0) {
         mbar_arrive_cluster(g_full_leader);
         mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->s_empty[b]), 0));
+      }
+    }
+    if (FUSED && blockIdx.y == 0) {
+      // ---- forward block sums: warp -> CTA -> global (f64 atomics), last CTA finalises ----
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        accM += __shfl_xor_sync(0xffffffffu, accM, o);
+        accD += __shfl_xor_sync(0xffffffffu, accD, o);
+      }
+      if (lane == 0) {
+        ctl->red[ew][0] = accM;
+        ctl->red[ew][1] = accD;
+      }
+      named_barrier_sync(1, BWD_EPI_THREADS);
+      if (et == 0) {
+        double m = 0.0, dd = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          m += ctl->red[k][0];
+          dd += ctl->red[k][1];
+        }
+        atomicAdd(p.acc + 0, m);
+        atomicAdd(p.acc + 1, dd);
+        __threadfence();
+        const unsigned t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+          __threadfence();
+          const double Mv = atomicAdd(p.acc + 0, 0.0);
+          const double Ds = atomicAdd(p.acc + 1, 0.0);
+          if (p.partial) {
+            p.partial[0] = Mv;
+            p.partial[1] = Ds;
+          }
+          if (p.finalize) write_final_stats(Mv, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats_out);
+        }
       }
     }
     // ---- row sums of G: 4 partials per row (2 column halves x 2 lane halves) -> all 128 rows in both CTAs ----
@@ -1455,10 +1525,13 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const int ch = ew >> 2;
     const int tl = lg * 32 + lane;                           // feature lane of the M-tile
     const float *rs_all = reinterpret_cast<const float *>(&ctl->colinfo[1][0]);
-    const float M = p.stats[EDRL_MMD_STAT_M];
-    const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
-    const float coef = 4.f * sgn * p.grad_out[0];
-    int rows_here = p.row_count - panel * BM;
+    float coef = 1.f;                                        // FUSED: U is written unscaled
+    if (!FUSED) {
+      const float M = p.stats[EDRL_MMD_STAT_M];
+      const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
+      coef = 4.f * sgn * p.grad_out[0];
+    }
+    int rows_here = rng_count - lpanel * BM;
     if (rows_here > BM) rows_here = BM;
     if (p.n - row_base < rows_here) rows_here = p.n - row_base;
     mbar_wait(&ctl->dz_full, 0);
@@ -1475,7 +1548,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         tmem_ld_wait();
         if (f_ok) {
           const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
-          float *oc = p.dz + (size_t)(row_base - p.row_begin + i0) * p.d + f;
+          float *oc = p.dz + (size_t)(out_row0 + i0) * p.d + f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (i0 + j < rows_here)
@@ -1541,11 +1614,8 @@ static int launch_fwd_t(const CUtensorMap &tm_hi, const CUtensorMap &tm_lo, cons
                         cudaStream_t st) {
   using Cfg = FwdCfg<SPLIT3>;
   auto kern = mmd_fwd_kernel<SPLIT3, MODE, FAST>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  // per launch (cheap): the attribute is per device, a process may drive several
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<grid, FWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_hi, tm_lo, p);
   EDRL_LAUNCHED();
   return 0;
@@ -1604,11 +1674,8 @@ static int forward_impl(int mode, const float *X, const float *Y, int n_s, int n
     int pairs = sms / 2;
     if (q2 < pairs) pairs = (int)(q2 > 0 ? q2 : 1);
     auto kern = fast ? mmd_fwd_pair_kernel<true> : mmd_fwd_pair_kernel<false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[fast ? 1 : 0]) {
-      EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
-      attr_done[fast ? 1 : 0] = true;
-    }
+    // per launch (cheap): the attribute is per device, a process may drive several
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_BYTES));
     kern<<<2 * pairs, F2_THREADS, F2_SMEM_BYTES, st>>>(tm_hi, p);
     EDRL_LAUNCHED();
     return 0;
@@ -1623,26 +1690,39 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
                         const BwdParams &p, dim3 grid, cudaStream_t st) {
   using Cfg = BwdCfg<SPLIT3>;
   auto kern = mmd_bwd_kernel<SPLIT3, FAST>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  // per launch (cheap): the attribute is per device, a process may drive several
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, c, d4, p);
   EDRL_LAUNCHED();
   return 0;
 }
 
-template <bool FAST, int RES>
+
+// dZ[i, f] = g sign(M) 4 (U[i, f] + c n z_i[f]) -- the closed-form bandwidth term on top of the fused pass
+__global__ void __launch_bounds__(256)
+mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ stats,
+                      const float *__restrict__ grad_out, int row_begin, int row_count, int row_begin2, int row_count2,
+                      int d, int d_pad, int n, float *__restrict__ dz) {
+  const float M = stats[EDRL_MMD_STAT_M];
+  const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
+  const float coef = 4.f * sgn * grad_out[0];
+  const float cn = stats[EDRL_MMD_STAT_C] * (float)n;
+  const size_t total = (size_t)(row_count + row_count2) * d;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / d;
+    const int f = (int)(i - r * d);
+    const size_t gr = (r < (size_t)row_count) ? (size_t)row_begin + r : (size_t)row_begin2 + (r - row_count);
+    dz[i] = coef * fmaf(cn, __ldg(zhi + gr * d_pad + f), U[i]);
+  }
+}
+
+template <bool FAST, int RES, bool FUSED = false>
 static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt, const BwdParams &p, dim3 grid,
                              cudaStream_t st) {
   using Cfg = Bwd2Cfg<RES>;
-  auto kern = mmd_bwd_pair_kernel<FAST, RES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  auto kern = mmd_bwd_pair_kernel<FAST, RES, FUSED>;
+  // per launch (cheap): the attribute is per device, a process may drive several
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_z64, tm_zt, p);
   EDRL_LAUNCHED();
   return 0;
@@ -1718,6 +1798,8 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
   p.zlo = reinterpret_cast<const float *>(ws + L.off_zlo);
   p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
+  p.acc = nullptr; p.ticket = nullptr; p.partial = nullptr; p.loss = nullptr; p.stats_out = nullptr;
+  p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0;
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
   if (!L.split3 && !legacy) {
@@ -1751,6 +1833,68 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   }
   if (fast) return launch_bwd_t<false, true>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
   return launch_bwd_t<false, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+}
+
+int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
+                          int flags, int row_begin, int row_count, int row_begin2, int row_count2, int finalize,
+                          float *loss, float *stats, double *partial, float *U, void *workspace,
+                          size_t workspace_bytes, void *stream) {
+  EDRL_CHECK_ARG(X && Y && U, "MK_MMD forward_grad: null argument");
+  EDRL_CHECK_ARG((flags & EDRL_MMD_3XTF32) == 0, "MK_MMD forward_grad: the fused pass is TF32 only");
+  Layout L = make_layout(n_s, n_t, d, flags);
+  if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
+  EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n,
+                 "MK_MMD forward_grad: row range [%d, %d) outside [0, %d)", row_begin, row_begin + row_count, L.n);
+  EDRL_CHECK_ARG(row_count2 == 0 || (row_begin2 >= row_begin + row_count && row_begin2 + row_count2 <= L.n),
+                 "MK_MMD forward_grad: second row range [%d, %d) must follow the first and end inside [0, %d)",
+                 row_begin2, row_begin2 + row_count2, L.n);
+  EDRL_CHECK_ARG(finalize ? (loss && stats) : (partial != nullptr), "MK_MMD forward_grad: null output");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  if (int rc = run_prep(X, Y, n_s, n_t, d, L, ws, st)) return rc;
+  CUtensorMap tm_z64, tm_zt;
+  if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
+  if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
+  BwdParams p;
+  p.n = L.n; p.n_s = n_s; p.n_pad = L.n_pad; p.d = d; p.d_pad = L.d_pad;
+  p.nb = L.n_pad / BN; p.kchunks = L.d_pad / BK; p.num = kernel_num; p.mul = kernel_mul;
+  p.row_begin = row_begin; p.row_count = row_count;
+  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
+  p.a = reinterpret_cast<const float *>(ws + L.off_a);
+  p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  p.zlo = nullptr;
+  p.stats = nullptr; p.grad_out = nullptr; p.dz = U;
+  p.acc = reinterpret_cast<double *>(ws + L.off_acc);
+  p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
+  p.partial = partial; p.loss = loss; p.stats_out = stats;
+  p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
+  dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS);
+  const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
+  if (L.d_pad <= 512) {
+    if (fast) return launch_bwd_pair_t<true, 8, true>(tm_z64, tm_zt, p, grid2, st);
+    return launch_bwd_pair_t<false, 8, true>(tm_z64, tm_zt, p, grid2, st);
+  }
+  if (fast) return launch_bwd_pair_t<true, 0, true>(tm_z64, tm_zt, p, grid2, st);
+  return launch_bwd_pair_t<false, 0, true>(tm_z64, tm_zt, p, grid2, st);
+}
+
+int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, const float *grad_out,
+                        const float *U, int row_begin, int row_count, int row_begin2, int row_count2, float *dZ,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_CHECK_ARG(stats && grad_out && U && dZ && workspace, "MK_MMD apply_grad: null argument");
+  Layout L = make_layout(n_s, n_t, d, flags);
+  EDRL_CHECK_ARG(workspace_bytes >= L.total, "MK_MMD apply_grad: workspace too small");
+  EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n, "MK_MMD apply_grad: bad row range");
+  const uint8_t *ws = reinterpret_cast<const uint8_t *>(workspace);
+  const size_t total = (size_t)(row_count + row_count2) * d;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = 8 * (device_sm_count() > 0 ? device_sm_count() : 148);
+  if (blocks > cap) blocks = cap;
+  mmd_apply_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      U, reinterpret_cast<const float *>(ws + L.off_zhi), stats, grad_out, row_begin, row_count, row_begin2, row_count2,
+      d, L.d_pad, L.n, dZ);
+  EDRL_LAUNCHED();
+  return 0;
 }
 
 }  // extern "C"

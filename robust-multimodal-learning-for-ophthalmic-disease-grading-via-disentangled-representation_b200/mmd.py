@@ -20,6 +20,9 @@ FLAG_3XTF32 = 1
 _PRECISIONS = {"tf32": FLAG_TF32, "3xtf32": FLAG_3XTF32}
 _default_precision = os.environ.get("EDRL_MMD_PRECISION", "tf32").lower()
 NUM_STATS = 8
+# TF32 training steps use the fused pass (forward sums + gradient in one sweep over the Gram tiles);
+# EDRL_MMD_FUSED=0 falls back to the separate forward and tile-recomputing backward kernels.
+_FUSED = os.environ.get("EDRL_MMD_FUSED", "1") != "0"
 
 
 def set_default_precision(name: str) -> None:
@@ -78,9 +81,18 @@ class _MKMMDFunction(torch.autograd.Function):
         ws = Workspace(n_s, n_t, d, flags, x.device)
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x.device)
-        _lib.check(lib.edrl_mmd_forward(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul), int(kernel_num),
-                                        flags, 0, 1, loss.data_ptr(), stats.data_ptr(), None, ws.ptr, ws.nbytes,
-                                        stream))
+        ctx.U = None
+        if _FUSED and flags == FLAG_TF32 and any(ctx.needs_input_grad[:2]):
+            # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
+            u = torch.empty(n_s + n_t, d, dtype=torch.float32, device=x.device)
+            _lib.check(lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul),
+                                                 int(kernel_num), flags, 0, n_s + n_t, 0, 0, 1, loss.data_ptr(),
+                                                 stats.data_ptr(), None, u.data_ptr(), ws.ptr, ws.nbytes, stream))
+            ctx.U = u
+        else:
+            _lib.check(lib.edrl_mmd_forward(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul),
+                                            int(kernel_num), flags, 0, 1, loss.data_ptr(), stats.data_ptr(), None,
+                                            ws.ptr, ws.nbytes, stream))
         ctx.ws = ws
         ctx.stats = stats
         ctx.shape = (n_s, n_t, d)
@@ -97,6 +109,13 @@ class _MKMMDFunction(torch.autograd.Function):
             return None, None, None, None, None
         g = grad_out.to(torch.float32).contiguous()
         stream = _lib.stream_and_device(g)
+        if ctx.U is not None:
+            dz = torch.empty_like(ctx.U)
+            _lib.check(lib.edrl_mmd_apply_grad(n_s, n_t, d, flags, ctx.stats.data_ptr(), g.data_ptr(),
+                                               ctx.U.data_ptr(), 0, n_s + n_t, 0, 0, dz.data_ptr(), ctx.ws.ptr,
+                                               ctx.ws.nbytes, stream))
+            return (dz[:n_s] if ctx.needs_input_grad[0] else None,
+                    dz[n_s:] if ctx.needs_input_grad[1] else None, None, None, None)
         # rows of Z = [X; Y]: only compute the row range that needs a gradient
         r0 = 0 if ctx.needs_input_grad[0] else n_s
         r1 = n_s + n_t if ctx.needs_input_grad[1] else n_s

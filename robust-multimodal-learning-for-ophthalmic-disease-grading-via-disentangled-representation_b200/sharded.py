@@ -17,7 +17,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .mmd import NUM_STATS, Workspace, _flags
+from . import mmd as _mmd
+from .mmd import FLAG_TF32, NUM_STATS, Workspace, _flags
 
 TILE = 128   # Gram tile edge of csrc/mmd.cu (BM = BN)
 
@@ -93,9 +94,19 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         partial = torch.zeros(2, dtype=torch.float64, device=x_all.device)
         loss = torch.empty((), dtype=torch.float32, device=x_all.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x_all.device)
-        _lib.check(lib.edrl_mmd_forward(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
-                                        float(kernel_mul), int(kernel_num), flags, rank, world, None, None,
-                                        partial.data_ptr(), ws.ptr, ws.nbytes, stream))
+        ctx.U = None
+        if _mmd._FUSED and flags == FLAG_TF32 and any(ctx.needs_input_grad[:2]):
+            # fused pass over this rank's rows (source rows, then target rows): partial sums + gradient part U
+            (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
+            u = torch.empty(c0 + c1, d, dtype=torch.float32, device=x_all.device)
+            _lib.check(lib.edrl_mmd_forward_grad(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
+                                                 float(kernel_mul), int(kernel_num), flags, r0, c0, r1, c1, 0, None,
+                                                 None, partial.data_ptr(), u.data_ptr(), ws.ptr, ws.nbytes, stream))
+            ctx.U = u
+        else:
+            _lib.check(lib.edrl_mmd_forward(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
+                                            float(kernel_mul), int(kernel_num), flags, rank, world, None, None,
+                                            partial.data_ptr(), ws.ptr, ws.nbytes, stream))
         reduce_partials(partial, group)
         _lib.check(lib.edrl_mmd_finalize(partial.data_ptr(), plan.n_s, plan.n_t, float(kernel_mul), int(kernel_num),
                                          loss.data_ptr(), stats.data_ptr(), ws.ptr, ws.nbytes, stream))
@@ -112,6 +123,14 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         mul, num, flags = ctx.hyper
         g = grad_out.to(torch.float32).contiguous()
         stream = _lib.stream_and_device(g)
+        if ctx.U is not None:
+            (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
+            dz = torch.empty_like(ctx.U)
+            _lib.check(lib.edrl_mmd_apply_grad(plan.n_s, plan.n_t, d, flags, ctx.stats.data_ptr(), g.data_ptr(),
+                                               ctx.U.data_ptr(), r0, c0, r1, c1, dz.data_ptr(), ctx.ws.ptr,
+                                               ctx.ws.nbytes, stream))
+            return (dz[:c0] if ctx.needs_input_grad[0] else None, dz[c0:] if ctx.needs_input_grad[1] else None,
+                    None, None, None, None)
         outs = []
         for need, (r0, cnt) in ((ctx.needs_input_grad[0], plan.source_rows()),
                                 (ctx.needs_input_grad[1], plan.target_rows())):

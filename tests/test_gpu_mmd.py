@@ -249,3 +249,45 @@ def test_midsize_vs_oracle(mode):
     gmax = max(np.abs(dx).max(), np.abs(dy).max())
     assert np.abs(xt.grad.cpu().numpy() - dx).max() <= gtol * gmax
     assert np.abs(yt.grad.cpu().numpy() - dy).max() <= gtol * gmax
+
+
+# ---------------------------------------------------------------- fused forward + gradient pass (TF32)
+@pytest.mark.parametrize("ns,nt,d", [(300, 212, 96), (37, 53, 24), (1024, 1024, 512), (200, 200, 700)])
+def test_fused_pass_matches_separate_kernels_and_oracle(raw, ns, nt, d):
+    from gpu_util import raw_apply_grad, raw_forward_grad
+    rng = np.random.default_rng(ns + d)
+    x = rng.standard_normal((ns, d)).astype(np.float32)
+    y = (rng.standard_normal((nt, d)) * 1.2 + 0.1).astype(np.float32)
+    xd, yd = dev(x), dev(y)
+    n = ns + nt
+    # separate forward + tile-recomputing backward
+    loss0, stats0, _, ws0 = raw.forward(xd, yd, flags=0)
+    dz0 = raw.backward(ns, nt, d, stats0, ws0, 0, n, grad_out=1.5, flags=0)
+    # fused
+    loss1, stats1, _, u, ws1 = raw_forward_grad(raw, xd, yd, 0, n)
+    dz1 = raw_apply_grad(raw, ns, nt, d, stats1, u, ws1, 0, n, grad_out=1.5)
+    torch.cuda.synchronize()
+    assert np.isclose(loss1.item(), loss0.item(), rtol=1e-5)
+    np.testing.assert_allclose(stats1.cpu().numpy()[:5], stats0.cpu().numpy()[:5], rtol=1e-4, atol=1e-9)
+    gmax = dz0.abs().max().item()
+    # two TF32-level evaluations (the separate backward rounds G including c, the fused pass adds c in closed form)
+    assert (dz1 - dz0).abs().max().item() <= 2e-3 * gmax, (dz1 - dz0).abs().max().item() / gmax
+    ref, _, dx, dy = O.mk_mmd_grad(x.astype(np.float64), y.astype(np.float64), grad_out=1.5)
+    assert np.isclose(loss1.item(), ref, rtol=1e-3, atol=1e-6)
+    gm = max(np.abs(dx).max(), np.abs(dy).max())
+    assert np.abs(dz1.cpu().numpy() - np.concatenate([dx, dy])).max() <= 2e-3 * gm
+    # two row ranges, partial sums only (what one rank of a sharded evaluation runs), summed over 2 "ranks"
+    h_s, h_t = ns // 2, nt // 2
+    tot = torch.zeros(2, dtype=torch.float64, device="cuda")
+    pieces = []
+    for (r0, c0, r1, c1) in ((0, h_s, ns, h_t), (h_s, ns - h_s, ns + h_t, nt - h_t)):
+        _, _, part, u2, ws2 = raw_forward_grad(raw, xd, yd, r0, c0, r1, c1, finalize=0)
+        tot += part
+        pieces.append((r0, c0, r1, c1, u2, ws2))
+    l2, s2 = raw.finalize(tot, ns, nt, pieces[-1][5])
+    torch.cuda.synchronize()
+    assert np.isclose(l2.item(), loss1.item(), rtol=1e-6)
+    for (r0, c0, r1, c1, u2, ws2) in pieces:
+        dzp = raw_apply_grad(raw, ns, nt, d, s2, u2, ws2, r0, c0, r1, c1, grad_out=1.5)
+        np.testing.assert_allclose(dzp[:c0].cpu().numpy(), dz1[r0:r0 + c0].cpu().numpy(), rtol=0, atol=1e-6 * gmax)
+        np.testing.assert_allclose(dzp[c0:].cpu().numpy(), dz1[r1:r1 + c1].cpu().numpy(), rtol=0, atol=1e-6 * gmax)
