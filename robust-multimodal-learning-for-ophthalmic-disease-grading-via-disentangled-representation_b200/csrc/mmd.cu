@@ -1204,7 +1204,10 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;   // row of dz this panel starts at
   const int row_base = rng_begin + lpanel * BM;           // first global row of the pair's 128-row panel
   const int f0 = blockIdx.y * P2_FEATS;                   // first feature column of this pass
-  const int nJ = p.nb;
+  // gridDim.z splits the column (J) range: slab z sweeps J tiles [J0, J0 + nJ) and writes its own partial output
+  // slab (summed by edrl_mmd_apply_grad).  128 panels on 74 SM pairs are two waves; four slabs make it 1.75.
+  const int J0 = (int)(((long long)blockIdx.z * p.nb) / gridDim.z);
+  const int nJ = (int)(((long long)(blockIdx.z + 1) * p.nb) / gridDim.z) - J0;
   const int kchunks = p.kchunks;                          // even (d_pad is a multiple of 64)
   const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;         // M-tiles of 256 features that hold real columns
   const int nres = (kchunks < RES) ? kchunks : RES;       // resident chunks of Z_I (even)
@@ -1268,7 +1271,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           tma_load_2d_pair_elect(zi_smem + kc * P2_CHUNK, &tm_z64, bar, kc * BK, irow);
       }
       auto load_S = [&](int J) {
-        const int jrow = J * BN + (int)rank * 64;
+        const int jrow = (J0 + J) * BN + (int)rank * 64;
         for (int kc = 0; kc < nres; kc += 2) {           // Z_I resident: a stage carries two chunks of Z_J
           uint8_t *st = acquire();
           const uint32_t bar = full0 + 8u * (uint32_t)s;
@@ -1289,7 +1292,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           for (int a4 = 0; a4 < BN / BK; ++a4) {
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_zt, bar, J * BN + a4 * BK, f0 + t * 256 + (int)rank * 128);
+            tma_load_2d_pair_elect(st, &tm_zt, bar, (J0 + J) * BN + a4 * BK, f0 + t * 256 + (int)rank * 128);
             next();
           }
       };
@@ -1420,7 +1423,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       const int b = J & 1;
       const uint32_t u = (uint32_t)(J >> 1);
       if (et < BN) {
-        const int gj = J * BN + et;
+        const int gj = (J0 + J) * BN + et;
         ctl->colinfo[b][et] = make_float2((float)p.racc[gj], p.a[gj]);
       }
       named_barrier_sync(1, BWD_EPI_THREADS);
@@ -1491,7 +1494,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         atomicAdd(p.acc + 1, dd);
         __threadfence();
         const unsigned t = atomicAdd(p.ticket, 1u);
-        if (t == gridDim.x - 1) {
+        if (t == gridDim.x * gridDim.z - 1) {
           __threadfence();
           const double Mv = atomicAdd(p.acc + 0, 0.0);
           const double Ds = atomicAdd(p.acc + 1, 0.0);
@@ -1548,7 +1551,7 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         tmem_ld_wait();
         if (f_ok) {
           const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
-          float *oc = p.dz + (size_t)(out_row0 + i0) * p.d + f;
+          float *oc = p.dz + ((size_t)blockIdx.z * (size_t)(p.row_count + p.row_count2) + out_row0 + i0) * p.d + f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (i0 + j < rows_here)
@@ -1702,7 +1705,7 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 __global__ void __launch_bounds__(256)
 mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ stats,
                       const float *__restrict__ grad_out, int row_begin, int row_count, int row_begin2, int row_count2,
-                      int d, int d_pad, int n, float *__restrict__ dz) {
+                      int d, int d_pad, int n, int nslab, float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
@@ -1712,7 +1715,9 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
     const size_t r = i / d;
     const int f = (int)(i - r * d);
     const size_t gr = (r < (size_t)row_count) ? (size_t)row_begin + r : (size_t)row_begin2 + (r - row_count);
-    dz[i] = coef * fmaf(cn, __ldg(zhi + gr * d_pad + f), U[i]);
+    float u = U[i];
+    for (int sl = 1; sl < nslab; ++sl) u += U[(size_t)sl * total + i];       // partial slabs of the J-split sweep
+    dz[i] = coef * fmaf(cn, __ldg(zhi + gr * d_pad + f), u);
   }
 }
 
@@ -1835,6 +1840,21 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   return launch_bwd_t<false, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
 }
 
+int edrl_mmd_grad_slabs(int n_s, int n_t, int rows) {
+  // The fused pass can split its column sweep into slabs (gridDim.z) with one partial output each.  Measured at
+  // N=8192, d=512 (128 panels on 74 SM pairs): 1 slab 1.165 ms, 2 -> 1.21, 4 -> 1.18, 8 -> 1.37: the sweep is bound by
+  // the chip-wide L2 -> SM rate, so a short last wave already runs faster per cluster and splitting only adds
+  // set-up and output traffic.  Default 1; EDRL_MMD_SLABS overrides for experiments.
+  if (n_s <= 0 || n_t <= 0 || rows <= 0) return 1;
+  static const char *env = getenv("EDRL_MMD_SLABS");
+  if (env) {
+    const int v = atoi(env);
+    const int nJ = (int)align_up((size_t)n_s + n_t, 256) / BN;
+    if (v > 1 && nJ / v >= 1) return v;
+  }
+  return 1;
+}
+
 int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                           int flags, int row_begin, int row_count, int row_begin2, int row_count2, int finalize,
                           float *loss, float *stats, double *partial, float *U, void *workspace,
@@ -1868,7 +1888,8 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
   p.partial = partial; p.loss = loss; p.stats_out = stats;
   p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
-  dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS);
+  dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS,
+             edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2));
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   if (L.d_pad <= 512) {
     if (fast) return launch_bwd_pair_t<true, 8, true>(tm_z64, tm_zt, p, grid2, st);
@@ -1892,7 +1913,7 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   if (blocks > cap) blocks = cap;
   mmd_apply_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       U, reinterpret_cast<const float *>(ws + L.off_zhi), stats, grad_out, row_begin, row_count, row_begin2, row_count2,
-      d, L.d_pad, L.n, dZ);
+      d, L.d_pad, L.n, edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2), dZ);
   EDRL_LAUNCHED();
   return 0;
 }

@@ -84,7 +84,8 @@ class _MKMMDFunction(torch.autograd.Function):
         ctx.U = None
         if _FUSED and flags == FLAG_TF32 and any(ctx.needs_input_grad[:2]):
             # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
-            u = torch.empty(n_s + n_t, d, dtype=torch.float32, device=x.device)
+            slabs = int(lib.edrl_mmd_grad_slabs(n_s, n_t, n_s + n_t))
+            u = torch.empty(slabs, n_s + n_t, d, dtype=torch.float32, device=x.device)
             _lib.check(lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul),
                                                  int(kernel_num), flags, 0, n_s + n_t, 0, 0, 1, loss.data_ptr(),
                                                  stats.data_ptr(), None, u.data_ptr(), ws.ptr, ws.nbytes, stream))
@@ -110,7 +111,7 @@ class _MKMMDFunction(torch.autograd.Function):
         g = grad_out.to(torch.float32).contiguous()
         stream = _lib.stream_and_device(g)
         if ctx.U is not None:
-            dz = torch.empty_like(ctx.U)
+            dz = torch.empty_like(ctx.U[0])
             _lib.check(lib.edrl_mmd_apply_grad(n_s, n_t, d, flags, ctx.stats.data_ptr(), g.data_ptr(),
                                                ctx.U.data_ptr(), 0, n_s + n_t, 0, 0, dz.data_ptr(), ctx.ws.ptr,
                                                ctx.ws.nbytes, stream))

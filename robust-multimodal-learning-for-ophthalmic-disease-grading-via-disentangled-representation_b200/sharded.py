@@ -98,7 +98,8 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         if _mmd._FUSED and flags == FLAG_TF32 and any(ctx.needs_input_grad[:2]):
             # fused pass over this rank's rows (source rows, then target rows): partial sums + gradient part U
             (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
-            u = torch.empty(c0 + c1, d, dtype=torch.float32, device=x_all.device)
+            slabs = int(lib.edrl_mmd_grad_slabs(plan.n_s, plan.n_t, c0 + c1))
+            u = torch.empty(slabs, c0 + c1, d, dtype=torch.float32, device=x_all.device)
             _lib.check(lib.edrl_mmd_forward_grad(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
                                                  float(kernel_mul), int(kernel_num), flags, r0, c0, r1, c1, 0, None,
                                                  None, partial.data_ptr(), u.data_ptr(), ws.ptr, ws.nbytes, stream))
@@ -125,7 +126,7 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         stream = _lib.stream_and_device(g)
         if ctx.U is not None:
             (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
-            dz = torch.empty_like(ctx.U)
+            dz = torch.empty_like(ctx.U[0])
             _lib.check(lib.edrl_mmd_apply_grad(plan.n_s, plan.n_t, d, flags, ctx.stats.data_ptr(), g.data_ptr(),
                                                ctx.U.data_ptr(), r0, c0, r1, c1, dz.data_ptr(), ctx.ws.ptr,
                                                ctx.ws.nbytes, stream))

@@ -1,11 +1,15 @@
 #!/bin/bash
-# ncu evidence for the bench command (B200_PROFILING.md recipe): plain run first, then the launch list,
-# then one --set full capture of the two MMD kernels.
+# ncu evidence for the bench command (B200_PROFILING.md recipe): plain run first, then the launch list of the same
+# command, then one --set full capture of the MMD kernels (fused training pass + loss-only forward), and one of the
+# Essence-Point select kernel.  Summaries are copied into profiles/ by tools/summarize_profiles.py (run locally).
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_pair_kernel" -s 6 -c 2 -o gpurun_out/prof_mmd_pair -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_pair_kernel" -s 8 -c 3 -o gpurun_out/prof_mmd_final -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
+python tools/run_topk.py > gpurun_out/plain_topk.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:topk_warp_radix -s 2 -c 2 -o gpurun_out/prof_topk_final -f python tools/run_topk.py > gpurun_out/ncu_topk.log 2>&1
+echo "topk capture rc=$?"
