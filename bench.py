@@ -282,6 +282,22 @@ def essence_point_extras(peaks):
         byts = 2 * B * kk * D * 4
         out["gather_rows"] = {"B": B, "T": T, "D": D, "k": kk, "ms": ms, "GB/s": byts / ms / 1e6,
                               "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]}
+        # the north-star's formulation: score per slice, top-k over the T slices, gather the k feature rows
+        scores = torch.randn(B, T, device="cuda")
+        for _ in range(2):
+            edrl_b200.select_gather(feat, scores, kk)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            edrl_b200.select_gather(feat, scores, kk)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        byts = B * T * 4 + B * kk * 8 + 2 * B * kk * D * 4
+        out["select_gather"] = {"B": B, "T": T, "D": D, "k": kk, "ms": ms, "GB/s": byts / ms / 1e6,
+                                "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
+                                "what": "topk_rows over [B,T] scores (sorted, indices bit-exact vs torch.topk) + "
+                                        "gather_rows of [B,k,D] features; bytes = scores + values/indices + 2 B k D 4"}
     except Exception as exc:   # extras never take the headline down
         out["error"] = repr(exc)
     return out

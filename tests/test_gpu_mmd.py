@@ -291,3 +291,72 @@ def test_fused_pass_matches_separate_kernels_and_oracle(raw, ns, nt, d):
         dzp = raw_apply_grad(raw, ns, nt, d, s2, u2, ws2, r0, c0, r1, c1, grad_out=1.5)
         np.testing.assert_allclose(dzp[:c0].cpu().numpy(), dz1[r0:r0 + c0].cpu().numpy(), rtol=0, atol=1e-6 * gmax)
         np.testing.assert_allclose(dzp[c0:].cpu().numpy(), dz1[r1:r1 + c1].cpu().numpy(), rtol=0, atol=1e-6 * gmax)
+
+
+# ---------------------------------------------------------------- host-side robustness: layouts, dtypes, streams, graphs
+def test_noncontiguous_bf16_inputs_and_side_stream():
+    import edrl_b200
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(200, 2 * 96, device="cuda", generator=g)
+    x = base[:, ::2]                                   # non-contiguous view
+    y = torch.randn(150, 96, device="cuda", generator=g) * 1.2 + 0.1
+    ref = edrl_b200.MK_MMD(x.contiguous(), y, precision="3xtf32").item()
+    assert np.isclose(edrl_b200.MK_MMD(x, y, precision="3xtf32").item(), ref, rtol=1e-6)
+    # bf16 inputs: computed in fp32 from the bf16 values, result cast back
+    xb, yb = x.contiguous().bfloat16().requires_grad_(True), y.bfloat16().requires_grad_(True)
+    lb = edrl_b200.MK_MMD(xb, yb)
+    assert lb.dtype == torch.bfloat16
+    lb.backward()
+    assert xb.grad.dtype == torch.bfloat16 and torch.isfinite(xb.grad.float()).all()
+    exact = edrl_b200.MK_MMD(xb.detach().float(), yb.detach().float(), precision="3xtf32").item()
+    assert np.isclose(lb.float().item(), exact, rtol=2e-2)
+    # work is enqueued on the current stream, whichever it is
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        xs = x.contiguous().requires_grad_(True)
+        ls = edrl_b200.MK_MMD(xs, y)
+        ls.backward()
+    s.synchronize()
+    xd = x.contiguous().requires_grad_(True)
+    ld = edrl_b200.MK_MMD(xd, y)
+    ld.backward()
+    torch.cuda.synchronize()
+    assert ls.item() == ld.item() and torch.equal(xs.grad, xd.grad)
+
+
+def test_cuda_graph_capture_of_a_training_step():
+    """The library only enqueues memsets and kernels on the caller's stream, so a fwd+bwd step is capturable."""
+    import edrl_b200
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # static inputs + warm-up on the capture stream
+        g = torch.Generator(device="cuda").manual_seed(9)
+        xs = torch.randn(512, 128, device="cuda", generator=g)
+        ys = torch.randn(384, 128, device="cuda", generator=g) * 1.3 + 0.2
+        for _ in range(2):
+            a = xs.clone().requires_grad_(True)
+            b = ys.clone().requires_grad_(True)
+            torch.autograd.grad(edrl_b200.MK_MMD(a, b), (a, b))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        a = xs.clone().requires_grad_(True)
+        b = ys.clone().requires_grad_(True)
+        l1 = edrl_b200.MK_MMD(a, b)
+        gx1, gy1 = torch.autograd.grad(l1, (a, b))
+    first = None
+    for scale in (1.0, 1.5):                           # replay on new data in the captured input buffers
+        xs.copy_(xs * scale)
+        graph.replay()
+        torch.cuda.synchronize()
+        xe = xs.clone().requires_grad_(True)
+        ye = ys.clone().requires_grad_(True)
+        l2 = edrl_b200.MK_MMD(xe, ye)
+        gx2, gy2 = torch.autograd.grad(l2, (xe, ye))
+        assert np.isclose(l1.item(), l2.item(), rtol=1e-6)
+        assert torch.allclose(gx1, gx2, rtol=1e-5, atol=1e-9) and torch.allclose(gy1, gy2, rtol=1e-5, atol=1e-9)
+        if first is None:
+            first = l1.item()
+    assert not np.isclose(first, l1.item(), rtol=1e-3)
