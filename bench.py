@@ -321,9 +321,7 @@ def essence_path_vs_torch_gpu():
             def ours():
                 zz = z.detach().requires_grad_(True)
                 pp = prox.detach().requires_grad_(True)
-                att, _ = edrl_b200.essence_scores(zz, pp[:, :Fd], torch.nn.functional.softplus(pp[:, Fd:]), eps)
-                loss, _, _ = edrl_b200.essence_select_loss(att, y, 100, sorted=False)
-                loss.backward()
+                edrl_b200.essence_train_loss(zz, pp, eps, y, 100).backward()
 
             def ref():
                 cpu_port.eprl_train_fwd_bwd(z, prox, eps, y, Fd)

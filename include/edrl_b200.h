@@ -174,6 +174,21 @@ int edrl_select_loss_bwd(const float *rowexp, const int32_t *pos_idx, const int3
                          const int64_t *y, const float *grad_out, int B, int C, int S, int k,
                          float *datt, void *stream);
 
+/* Fused train path of EPRL.forward after the encoder (fusion_net.py:137-150, 220-243): one call forward, one call
+ * backward -- the same kernels as the entry points above, launched back to back so the host issues 2 calls instead
+ * of 10 and never touches softplus / slicing ops.  proxies is the [C, 2F] parameter (mu | raw sigma; softplus with
+ * torch's threshold is applied in the kernel, fusion_net.py:116-119); eps [C,S,F]; y int64 [B].
+ *   saved   : edrl_essence_saved_floats() floats written by forward, read by backward
+ *   scratch : edrl_essence_scratch_floats() floats, backward only
+ *   dz [B,T,F] and/or dproxies [C,2F] may be NULL when not needed. */
+size_t edrl_essence_saved_floats(int B, int T, int F, int C, int S, int k);
+size_t edrl_essence_scratch_floats(int B, int T, int F, int C, int S, int k);
+int edrl_essence_train_fwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
+                           int F, int C, int S, int k, float *loss, float *saved, void *stream);
+int edrl_essence_train_bwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
+                           int F, int C, int S, int k, const float *saved, const float *grad_out, float *scratch,
+                           float *dz, float *dproxies, void *stream);
+
 /* North-star extension (no reference code, oracle = torch.topk o torch.gather):
  *   out[b, j, :] = features[b, idx[b,j], :],  features [B,T,D], idx [B,k] int32, out [B,k,D]. */
 int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T, int D, int k,

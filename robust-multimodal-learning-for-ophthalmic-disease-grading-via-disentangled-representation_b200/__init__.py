@@ -6,10 +6,11 @@ from . import _lib
 from .mmd import (MK_MMD, gaussian_kernel, compute_js_divergence, compute_kl_divergence, mk_mmd_with_stats,
                   set_default_precision, get_default_precision)
 from .sharded import sharded_MK_MMD, RowBlockPlan
-from .eprl import EPRL, essence_scores, essence_select_loss, topk_rows, gather_rows, select_gather
+from .eprl import (EPRL, essence_scores, essence_select_loss, essence_train_loss, topk_rows, gather_rows,
+                   select_gather)
 
 __all__ = ["MK_MMD", "gaussian_kernel", "compute_js_divergence", "compute_kl_divergence", "mk_mmd_with_stats",
-           "set_default_precision", "get_default_precision", "EPRL", "essence_scores", "essence_select_loss",
+           "set_default_precision", "get_default_precision", "EPRL", "essence_scores", "essence_select_loss", "essence_train_loss",
            "topk_rows", "gather_rows", "select_gather", "launch_count", "sharded_MK_MMD", "RowBlockPlan"]
 
 

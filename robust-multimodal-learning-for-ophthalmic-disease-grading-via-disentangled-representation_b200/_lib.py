@@ -54,6 +54,12 @@ PROTOTYPES = {
     "edrl_proxy_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "edrl_select_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
+    "edrl_essence_saved_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "edrl_essence_scratch_floats": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "edrl_essence_train_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p]),
+    "edrl_essence_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "edrl_gather_rows_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "edrl_gather_rows_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

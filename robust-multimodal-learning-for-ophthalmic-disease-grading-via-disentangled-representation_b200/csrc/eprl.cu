@@ -171,18 +171,24 @@ token_featmean_kernel(const float *__restrict__ z, const float *__restrict__ col
 }
 
 // ----------------------------------------------------------------------------- K5 proxies
-// grid (ceil(F/32), C), block (32, 32): lane -> feature, y -> sample slice
+// softplus exactly as torch.nn.functional.softplus (beta = 1, threshold = 20), code/fusion_net.py:118
+__device__ __forceinline__ float softplus_torch(float x) { return (x > 20.f) ? x : log1pf(expf(x)); }
+
+// grid (ceil(F/32), C), block (32, 32): lane -> feature, y -> sample slice.
+// mu / sigma rows are `ldp` floats apart; raw != 0: `sigma` holds the raw proxy half and softplus is applied here
+// (lets the fused entry point read the [C, 2F] proxies parameter directly).
 __global__ void __launch_bounds__(1024)
 proxy_normalize_fwd_kernel(const float *__restrict__ mu, const float *__restrict__ sigma,
-                           const float *__restrict__ eps, int S, int F, float *__restrict__ z_pn,
+                           const float *__restrict__ eps, int S, int F, int ldp, int raw, float *__restrict__ z_pn,
                            float *__restrict__ pnorm) {
   __shared__ float s_sq[32][33];
   const int f = blockIdx.x * 32 + threadIdx.x;
   const int c = blockIdx.y;
   float m = 0.f, sg = 0.f, sq = 0.f;
   if (f < F) {
-    m = mu[(size_t)c * F + f];
-    sg = sigma[(size_t)c * F + f];
+    m = mu[(size_t)c * ldp + f];
+    sg = sigma[(size_t)c * ldp + f];
+    if (raw) sg = softplus_torch(sg);
     const float *ep = eps + (size_t)c * S * F + f;
     for (int s = threadIdx.y; s < S; s += 32) {
       const float v = fmaf(sg, __ldg(ep + (size_t)s * F), m);
@@ -208,16 +214,20 @@ proxy_normalize_fwd_kernel(const float *__restrict__ mu, const float *__restrict
 __global__ void __launch_bounds__(1024)
 proxy_normalize_bwd_kernel(const float *__restrict__ mu, const float *__restrict__ sigma,
                            const float *__restrict__ eps, const float *__restrict__ pnorm,
-                           const float *__restrict__ dz_pn, int S, int F, float *__restrict__ dmu,
-                           float *__restrict__ dsigma) {
+                           const float *__restrict__ dz_pn, int S, int F, int ldp, int raw, int ldo,
+                           float *__restrict__ dmu, float *__restrict__ dsigma) {
   __shared__ float red[5][32][33];
   const int f = blockIdx.x * 32 + threadIdx.x;
   const int c = blockIdx.y;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
-  float m = 0.f, sg = 0.f;
+  float m = 0.f, sg = 0.f, chain = 1.f;
   if (f < F) {
-    m = mu[(size_t)c * F + f];
-    sg = sigma[(size_t)c * F + f];
+    m = mu[(size_t)c * ldp + f];
+    sg = sigma[(size_t)c * ldp + f];
+    if (raw) {
+      chain = 1.f / (1.f + expf(-sg));        // d softplus / d raw = sigmoid(raw) (1 beyond the threshold, to fp32)
+      sg = softplus_torch(sg);
+    }
     const float *ep = eps + (size_t)c * S * F + f;
     const float *gp = dz_pn + (size_t)c * S * F + f;
     for (int s = threadIdx.y; s < S; s += 32) {
@@ -248,8 +258,8 @@ proxy_normalize_bwd_kernel(const float *__restrict__ mu, const float *__restrict
     const float nrm = pnorm[(size_t)c * F + f];
     const float q = fmaxf(nrm, NORM_EPS);
     const float kk = (nrm > NORM_EPS) ? (t[2] / (q * q * nrm)) : 0.f;
-    dmu[(size_t)c * F + f] = t[0] / q - t[3] * kk;
-    dsigma[(size_t)c * F + f] = t[1] / q - t[4] * kk;
+    dmu[(size_t)c * ldo + f] = t[0] / q - t[3] * kk;
+    dsigma[(size_t)c * ldo + f] = (t[1] / q - t[4] * kk) * chain;
   }
 }
 
@@ -1158,7 +1168,7 @@ int edrl_proxy_normalize_fwd(const float *mu, const float *sigma, const float *e
   EDRL_CHECK_ARG(mu && sigma && eps && z_pn && pnorm, "proxy_normalize_fwd: null argument");
   EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_fwd: bad shape");
   dim3 grid((F + 31) / 32, C), block(32, 32);
-  proxy_normalize_fwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, S, F, z_pn, pnorm);
+  proxy_normalize_fwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, S, F, F, 0, z_pn, pnorm);
   EDRL_LAUNCHED();
   return 0;
 }
@@ -1168,7 +1178,7 @@ int edrl_proxy_normalize_bwd(const float *mu, const float *sigma, const float *e
   EDRL_CHECK_ARG(mu && sigma && eps && pnorm && dz_pn && dmu && dsigma, "proxy_normalize_bwd: null argument");
   EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_bwd: bad shape");
   dim3 grid((F + 31) / 32, C), block(32, 32);
-  proxy_normalize_bwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, pnorm, dz_pn, S, F, dmu, dsigma);
+  proxy_normalize_bwd_kernel<<<grid, block, 0, ST(stream)>>>(mu, sigma, eps, pnorm, dz_pn, S, F, F, 0, F, dmu, dsigma);
   EDRL_LAUNCHED();
   return 0;
 }
@@ -1267,6 +1277,96 @@ int edrl_gather_rows_bwd(const float *dout, const int32_t *idx, int B, int T, in
   gather_rows_bwd_kernel<<<B, 256, (size_t)T * sizeof(int), ST(stream)>>>(dout, idx, T, D, k,
                                                                           vec4_ok(dout, dfeatures, D), dfeatures);
   EDRL_LAUNCHED();
+  return 0;
+}
+
+/* ---- fused train path: one call forward, one call backward (the separate entry points above stay for the eval
+ *      branch and the tests).  `saved` is carved by ess_layout(); every segment starts 16-byte aligned. ---- */
+namespace {
+struct EssLayout {
+  size_t zbar, colsum, colnorm, z_pn, pnorm, att, vals, idx, rowexp, total;      // saved (floats)
+  size_t datt, dzbar, dz_pn, scratch_total;                                     // scratch (floats)
+};
+inline size_t up4(size_t v) { return (v + 3) / 4 * 4; }
+EssLayout ess_layout(int B, int T, int F, int C, int S, int k) {
+  (void)T;
+  EssLayout L;
+  size_t o = 0;
+  L.zbar = o;    o += up4((size_t)B * F);
+  L.colsum = o;  o += up4((size_t)B * F);
+  L.colnorm = o; o += up4((size_t)B * F);
+  L.z_pn = o;    o += up4((size_t)C * S * F);
+  L.pnorm = o;   o += up4((size_t)C * F);
+  L.att = o;     o += up4((size_t)B * C * S);
+  L.vals = o;    o += up4((size_t)2 * B * k);
+  L.idx = o;     o += up4((size_t)2 * B * k);
+  L.rowexp = o;  o += up4((size_t)B);
+  L.total = o;
+  o = 0;
+  L.datt = o;    o += up4((size_t)B * C * S);
+  L.dzbar = o;   o += up4((size_t)B * F);
+  L.dz_pn = o;   o += up4((size_t)C * S * F);
+  L.scratch_total = o;
+  return L;
+}
+}  // namespace
+
+size_t edrl_essence_saved_floats(int B, int T, int F, int C, int S, int k) {
+  if (B <= 0 || T <= 0 || F <= 0 || C < 2 || S <= 0 || k <= 0) return 0;
+  return ess_layout(B, T, F, C, S, k).total;
+}
+size_t edrl_essence_scratch_floats(int B, int T, int F, int C, int S, int k) {
+  if (B <= 0 || T <= 0 || F <= 0 || C < 2 || S <= 0 || k <= 0) return 0;
+  return ess_layout(B, T, F, C, S, k).scratch_total;
+}
+
+int edrl_essence_train_fwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
+                           int F, int C, int S, int k, float *loss, float *saved, void *stream) {
+  EDRL_CHECK_ARG(z && proxies && eps && y && loss && saved, "essence_train_fwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && F > 0 && C >= 2 && S > 0, "essence_train_fwd: bad shape");
+  EDRL_CHECK_ARG(k >= 1 && k <= S, "selected index k out of range (k=%d, row width %d)", k, S);
+  const EssLayout L = ess_layout(B, T, F, C, S, k);
+  float *vals = saved + L.vals;
+  int32_t *idx = reinterpret_cast<int32_t *>(saved + L.idx);
+  if (int rc = edrl_token_stats_fwd(z, B, T, F, saved + L.zbar, saved + L.colsum, saved + L.colnorm, stream)) return rc;
+  {
+    dim3 grid((F + 31) / 32, C), block(32, 32);
+    proxy_normalize_fwd_kernel<<<grid, block, 0, ST(stream)>>>(proxies, proxies + F, eps, S, F, 2 * F, 1,
+                                                               saved + L.z_pn, saved + L.pnorm);
+    EDRL_LAUNCHED();
+  }
+  if (int rc = edrl_score_fwd(saved + L.zbar, saved + L.z_pn, B, C * S, F, saved + L.att, stream)) return rc;
+  if (int rc = edrl_select_topk_fwd(saved + L.att, y, B, C, S, k, /*sorted=*/0, vals, idx, vals + (size_t)B * k,
+                                    idx + (size_t)B * k, stream))
+    return rc;
+  return edrl_proxy_loss_fwd(vals, vals + (size_t)B * k, B, k, loss, saved + L.rowexp, stream);
+}
+
+int edrl_essence_train_bwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
+                           int F, int C, int S, int k, const float *saved, const float *grad_out, float *scratch,
+                           float *dz, float *dproxies, void *stream) {
+  EDRL_CHECK_ARG(z && proxies && eps && y && saved && grad_out && scratch, "essence_train_bwd: null argument");
+  EDRL_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && F > 0 && C >= 2 && S > 0 && k >= 1 && k <= S,
+                 "essence_train_bwd: bad shape");
+  const EssLayout L = ess_layout(B, T, F, C, S, k);
+  const int32_t *idx = reinterpret_cast<const int32_t *>(saved + L.idx);
+  if (int rc = edrl_select_loss_bwd(saved + L.rowexp, idx, idx + (size_t)B * k, y, grad_out, B, C, S, k,
+                                    scratch + L.datt, stream))
+    return rc;
+  if (int rc = edrl_score_bwd(scratch + L.datt, saved + L.zbar, saved + L.z_pn, B, C * S, F, dz ? scratch + L.dzbar : nullptr,
+                              dproxies ? scratch + L.dz_pn : nullptr, stream))
+    return rc;
+  if (dz) {
+    if (int rc = edrl_token_stats_bwd(z, saved + L.colsum, saved + L.colnorm, scratch + L.dzbar, B, T, F, dz, stream))
+      return rc;
+  }
+  if (dproxies) {
+    dim3 grid((F + 31) / 32, C), block(32, 32);
+    proxy_normalize_bwd_kernel<<<grid, block, 0, ST(stream)>>>(proxies, proxies + F, eps, saved + L.pnorm,
+                                                               scratch + L.dz_pn, S, F, 2 * F, 1, 2 * F, dproxies,
+                                                               dproxies + F);
+    EDRL_LAUNCHED();
+  }
   return 0;
 }
 

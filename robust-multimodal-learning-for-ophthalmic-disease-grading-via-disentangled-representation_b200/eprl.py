@@ -124,6 +124,58 @@ class _SelectLossFunction(torch.autograd.Function):
         return datt, None, None, None
 
 
+class _EssenceTrainFunction(torch.autograd.Function):
+    """The whole train-branch loss after the encoder (code/fusion_net.py:137-150, 220-243) as one C-ABI call forward
+    and one backward: proxy_loss(z, proxies, eps, y).  Same kernels as _ScoreFunction + _SelectLossFunction; softplus
+    on the raw proxy half is applied inside the proxy kernel."""
+
+    @staticmethod
+    def forward(ctx, z, proxies, eps, y, k):
+        lib = _lib.load()
+        z, proxies, eps = _f32c(z), _f32c(proxies), _f32c(eps)
+        B, T, Fd = z.shape
+        C, S, F2 = eps.shape
+        if F2 != Fd or proxies.shape != (C, 2 * Fd):
+            raise RuntimeError(f"EPRL: shape mismatch z{tuple(z.shape)} proxies{tuple(proxies.shape)} "
+                               f"eps{tuple(eps.shape)}")
+        y = y.to(device=z.device, dtype=torch.int64).contiguous()
+        st = _lib.stream_and_device(z)
+        saved = torch.empty(int(lib.edrl_essence_saved_floats(B, T, Fd, C, S, k)), device=z.device)
+        loss = torch.empty((), device=z.device)
+        _lib.check(lib.edrl_essence_train_fwd(z.data_ptr(), proxies.data_ptr(), eps.data_ptr(), y.data_ptr(), B, T, Fd,
+                                              C, S, k, loss.data_ptr(), saved.data_ptr(), st))
+        ctx.save_for_backward(z, proxies, eps, y, saved)
+        ctx.dims = (B, T, Fd, C, S, k)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gloss):
+        lib = _lib.load()
+        z, proxies, eps, y, saved = ctx.saved_tensors
+        B, T, Fd, C, S, k = ctx.dims
+        g = _f32c(gloss)
+        st = _lib.stream_and_device(z)
+        scratch = torch.empty(int(lib.edrl_essence_scratch_floats(B, T, Fd, C, S, k)), device=z.device)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        dprox = torch.empty_like(proxies) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.edrl_essence_train_bwd(z.data_ptr(), proxies.data_ptr(), eps.data_ptr(), y.data_ptr(), B, T, Fd,
+                                              C, S, k, saved.data_ptr(), g.data_ptr(), scratch.data_ptr(),
+                                              _lib.ptr(dz), _lib.ptr(dprox), st))
+        return dz, dprox, None, None, None
+
+
+def essence_train_loss(z, proxies, eps, y, k=SELF_TOPK):
+    """proxy_loss of the train branch from the encoder output z [B,T,F], the raw proxies parameter [C,2F]
+    (mu | pre-softplus sigma), the noise eps [C,S,F] and labels y [B] -- one fused call each way."""
+    _lib.require_cuda(z, proxies, eps)
+    if z.dim() != 3:
+        raise RuntimeError(f"EPRL expects token features [B, T, F], got {tuple(z.shape)}")
+    if k > eps.shape[1]:
+        raise RuntimeError("selected index k out of range")
+    return _EssenceTrainFunction.apply(z, proxies, eps, y, int(k))
+
+
 def essence_scores(z, mu, sigma, eps):
     """Differentiable att [B,C,S] (see _ScoreFunction); also returns the per-(b,f) token norms."""
     _lib.require_cuda(z, mu, sigma, eps)
@@ -336,8 +388,7 @@ class EPRL(nn.Module):
         if labels.numel() != B:
             raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
                              f"[{B}], [{labels.numel()}]")
-        att, _ = essence_scores(z, mu_proxy, sigma_proxy, eps_proxy)
-        proxy_loss, _, _ = essence_select_loss(att, labels, self.self_topk, sorted=False)
+        proxy_loss = essence_train_loss(z, self.proxies, eps_proxy, labels, self.self_topk)
         return mu_proxy.repeat(B, 1, 1), sigma_proxy.repeat(B, 1, 1), proxy_loss, z
 
     @staticmethod

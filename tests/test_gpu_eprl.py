@@ -136,6 +136,30 @@ def test_train_path_matches_reference_golden(key, ge):
     assert np.abs(zt.grad.cpu().numpy() - bw["dz"]).max() <= 2e-4 * np.abs(bw["dz"]).max()
 
 
+@pytest.mark.parametrize("key", ["small_f32", "tok144_f32", "tok216_f32"])
+def test_fused_train_call_matches_reference_golden(key, ge):
+    """edrl_essence_train_fwd/bwd (what EPRL.forward uses in training) against the reference's recorded outputs."""
+    import edrl_b200
+    z = ge[key + "_z"].astype(np.float32)
+    eps = ge[key + "_eps"].astype(np.float32)
+    prox = ge[key + "_proxies"].astype(np.float32)
+    y = ge[key + "_y"]
+    proxies = dev(prox).requires_grad_(True)
+    zt = dev(z).requires_grad_(True)
+    loss = edrl_b200.essence_train_loss(zt, proxies, dev(eps), torch.as_tensor(y).cuda(), 100)
+    (3.0 * loss).backward()
+    assert np.isclose(loss.item(), float(ge[key + "_loss"]), rtol=2e-4)
+    gz = 3.0 * ge[key + "_dz"]
+    assert np.abs(zt.grad.cpu().numpy() - gz).max() <= 2e-3 * np.abs(gz).max()
+    gp = 3.0 * ge[key + "_dproxies"]
+    assert np.abs(proxies.grad.cpu().numpy() - gp).max() <= 2e-3 * np.abs(gp).max()
+    # and bit-for-bit the same loss as the two-function path on the same inputs
+    zd = z.shape[2]
+    att, _ = edrl_b200.essence_scores(dev(z), dev(prox)[:, :zd], torch.nn.functional.softplus(dev(prox)[:, zd:]), dev(eps))
+    l2, _, _ = edrl_b200.essence_select_loss(att, torch.as_tensor(y).cuda(), 100, sorted=False)
+    assert np.isclose(loss.item(), l2.item(), rtol=1e-6)
+
+
 @pytest.mark.parametrize("key", ["tok144_f32", "tok216_f32"])
 def test_module_eval_branch_matches_reference_golden(key, ge):
     import edrl_b200
