@@ -83,3 +83,38 @@ def eprl_train_fwd_bwd(z, proxies, eps, y, z_dim, k=100):
     loss = torch.mean(torch.exp(-tp.mean(dim=1) + tn.mean(dim=1)))            # :240-243
     loss.backward()
     return loss.detach(), z.grad, proxies.grad
+
+
+def mk_mmd_graph(source, target, kernel_mul=2.0, kernel_num=5):
+    """code/MMD.py:46-74 as a differentiable torch expression (keeps the autograd graph; baseline arm of
+    examples/edrl_step_synthetic.py)."""
+    ns, nt = source.shape[0], target.shape[0]
+    n = ns + nt
+    z = torch.cat([source, target], dim=0)
+    sq = (z ** 2).sum(dim=1, keepdim=True)
+    dist2 = (sq + sq.t() - 2 * (z @ z.t())).clamp(min=0.0)
+    bw = dist2.sum() / (n * n - n)
+    bw = bw / kernel_mul ** (kernel_num // 2)
+    kmat = sum(torch.exp(-dist2 / (bw * kernel_mul ** i)) for i in range(kernel_num))
+    return (kmat[:ns, :ns].sum() / ns ** 2 + kmat[ns:, ns:].sum() / nt ** 2
+            - kmat[:ns, ns:].sum() / (ns * nt) - kmat[ns:, :ns].sum() / (ns * nt)).abs()
+
+
+def eprl_train_loss_graph(z, proxies, eps, y, z_dim, k=100):
+    """The train-branch proxy loss (code/fusion_net.py:137-150, 220-243) as a differentiable torch expression."""
+    import torch.nn.functional as F
+    b = z.shape[0]
+    mu = proxies[:, :z_dim]
+    sigma = F.softplus(proxies[:, z_dim:])
+    z_proxy = mu.unsqueeze(1) + sigma.unsqueeze(1) * eps
+    z_norm = F.normalize(z, dim=1)
+    zp_norm = F.normalize(z_proxy)
+    att = torch.matmul(z_norm.unsqueeze(1), zp_norm.unsqueeze(0).expand(b, -1, -1, -1).transpose(2, 3))
+    att = att.permute(0, 2, 1, 3).mean(dim=1)
+    mask = torch.zeros(b, att.shape[1], dtype=torch.bool, device=z.device)
+    mask[torch.arange(b, device=z.device), y] = True
+    pos = torch.masked_select(att, mask.unsqueeze(-1)).view(b, -1)
+    neg = torch.masked_select(att, ~mask.unsqueeze(-1)).view(b, -1)
+    tp, _ = torch.topk(pos, k, dim=1)
+    tn, _ = torch.topk(neg, k, dim=1)
+    return torch.mean(torch.exp(-tp.mean(dim=1) + tn.mean(dim=1)))
