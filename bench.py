@@ -373,6 +373,34 @@ def essence_path_vs_torch_gpu():
     return out
 
 
+def eval_missing_modality():
+    """BASELINE configs[4]: Essence-Point eval branch (pseudo-labels, no gradients) when one modality is missing,
+    i.e. its tokens come from a zero-filled input (the reference has no modality switch; zero filling is the closest
+    published semantics).  Volumes (samples) per second through EPRL.eval()."""
+    import edrl_b200
+    out = []
+    try:
+        for (name, T, xd) in (("oct_missing(zero OCT tokens)", 216, 768), ("fundus_missing(zero fundus tokens)", 144, 1024)):
+            for noise in ("reference", "device"):
+                for B in (16, 64):
+                    torch.manual_seed(0)
+                    m = edrl_b200.EPRL(xd, num_classes=2, sample_num=800, batch_size=B, noise=noise).cuda().eval()
+                    x = torch.zeros(B, T, xd, device="cuda")
+                    with torch.no_grad():
+                        for _ in range(3):
+                            m(x)
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        for _ in range(20):
+                            m(x)
+                        torch.cuda.synchronize()
+                    ms = (time.perf_counter() - t0) / 20 * 1e3
+                    out.append({"case": name, "noise": noise, "B": B, "ms": ms, "volumes_per_s": B / ms * 1e3})
+    except Exception as exc:
+        out.append({"error": repr(exc)})
+    return out
+
+
 def sweep_vs_torch_gpu(prec):
     """BASELINE configs[1]: MK_MMD fwd+bwd sweep, d=512, against the reference's torch op sequence run eagerly on
     the SAME GPU (oracle/cpu_port.mk_mmd_fwd_bwd is device agnostic) -- plus the reference's own training shape
@@ -654,7 +682,20 @@ def run_ours(args, rank, local_rank, world):
         if extras:
             line["essence_point"] = extras
             line["sweep_vs_torch_gpu"] = sweep_vs_torch_gpu(prec)
+            # the same step in the other precision mode (3xTF32 = hi/lo split, fp32-level accuracy: loss within 1e-6
+            # of the fp64 value; runs on the first-generation single-CTA kernels)
+            other = "3xtf32" if prec == "tf32" else "tf32"
+
+            def other_step():
+                x.grad = None
+                y.grad = None
+                edrl_b200.MK_MMD(x, y, precision=other).backward()
+
+            line["precision_modes"] = {prec: {"ms_per_step": ms_per_step, "value": value},
+                                       other: (lambda t: {"ms_per_step": t, "value": N / (t * 1e-3)})(
+                                           timed_steps(other_step, 5, 3, flush, 1) / 5)}
             line["essence_path_vs_torch_gpu"] = essence_path_vs_torch_gpu()
+            line["eval_missing_modality"] = eval_missing_modality()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1172,8 +1172,7 @@ struct Bwd2Ctrl {
   double red[8][2];               // FUSED: per-warp partial block sums
 };
 static_assert(sizeof(Bwd2Ctrl) <= P2_CTRL_BYTES, "Bwd2Ctrl does not fit its smem slot");
-static_assert(Bwd2Cfg<0>::SMEM_BYTES <= 232448 && Bwd2Cfg<8>::SMEM_BYTES <= 232448 && Bwd2Cfg<16>::SMEM_BYTES <= 232448,
-              "smem budget");
+static_assert(Bwd2Cfg<0>::SMEM_BYTES <= 232448 && Bwd2Cfg<8>::SMEM_BYTES <= 232448, "smem budget");
 
 // FUSED: the same pass also evaluates the forward block sums (M, D) in the epilogue and writes the
 // bandwidth-independent part of the gradient U_i = rowsum(G')_i z_i - (G' Z)_i with G' = -a_i a_j Q_ij / sigma_0 [L_raw >= 0];
@@ -1813,17 +1812,9 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
     if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
     if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
     dim3 grid2(2 * ((row_count + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS);
-    static const char *res_env = getenv("EDRL_MMD_BWD_RES");               // A/B switch for profiling: 0 | 8 | 16
-    int res = (L.d_pad <= 512) ? 8 : 0;
-    if (res_env && L.d_pad <= 512) res = atoi(res_env);
-    if (res == 16) {
-      if (fast) return launch_bwd_pair_t<true, 16>(tm_z64, tm_zt, p, grid2, st);
-      return launch_bwd_pair_t<false, 16>(tm_z64, tm_zt, p, grid2, st);
-    }
-    if (res == 12) {
-      if (fast) return launch_bwd_pair_t<true, 12>(tm_z64, tm_zt, p, grid2, st);
-      return launch_bwd_pair_t<false, 12>(tm_z64, tm_zt, p, grid2, st);
-    }
+    // resident Z_I chunks: 8 of 16 for d <= 512 (measured: 16 -> 1.22 ms, 12 -> 1.10 ms, 8 -> 1.05 ms, 0 -> 1.12 ms
+    // at N=8192, d=512: more residency leaves too few ring stages), none beyond
+    const int res = (L.d_pad <= 512) ? 8 : 0;
     if (res == 8) {
       if (fast) return launch_bwd_pair_t<true, 8>(tm_z64, tm_zt, p, grid2, st);
       return launch_bwd_pair_t<false, 8>(tm_z64, tm_zt, p, grid2, st);
