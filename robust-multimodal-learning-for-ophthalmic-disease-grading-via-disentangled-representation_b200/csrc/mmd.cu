@@ -41,7 +41,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct Layout {
   int n, n_pad, d_pad;
   bool split3;
-  size_t off_acc, off_colsum, off_r, off_a, off_zhi, off_zthi, off_zlo, off_ztlo, total;
+  size_t off_acc, off_colsum, off_colsum_hi, off_r, off_a, off_zhi, off_zthi, off_zlo, off_ztlo, total;
   size_t zero_bytes;  // [off_acc, off_acc + zero_bytes) must be cleared before prep
 };
 
@@ -53,7 +53,8 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.split3 = (flags & EDRL_MMD_3XTF32) != 0;
   size_t o = 0;
   L.off_acc = o;      o += 256;                                   // 8 doubles + ticket counter
-  L.off_colsum = o;   o += align_up((size_t)L.d_pad * 8, 256);    // double[d_pad]
+  L.off_colsum = o;   o += align_up((size_t)L.d_pad * 8, 256);    // double[d_pad]: column sums of [X; Y]
+  L.off_colsum_hi = o; o += align_up((size_t)L.d_pad * 8, 256);   // double[d_pad]: column sums of the centred TF32 copy
   L.off_r = o;        o += align_up((size_t)L.n_pad * 8, 256);    // double[n_pad]
   L.zero_bytes = o - L.off_acc;
   L.off_a = o;        o += align_up((size_t)L.n_pad * 4, 256);    // float[n_pad]
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256)
 prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int n_s, int n_t, int d, int n_pad,
                    int d_pad, const double *__restrict__ colsum, float *__restrict__ zhi, float *__restrict__ zthi,
                    float *__restrict__ zlo, float *__restrict__ ztlo, double *__restrict__ racc,
-                   float *__restrict__ a, double *__restrict__ acc) {
+                   float *__restrict__ a, double *__restrict__ acc, double *__restrict__ colsum_hi) {
   __shared__ float tile_hi[32][33];
   __shared__ float tile_lo[SPLIT3 ? 32 : 1][33];
   __shared__ float blk_sum[8];
@@ -129,6 +130,14 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
       const int cc = wy * 4 + k;
       zthi[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_hi[lane][cc];
       if (SPLIT3) ztlo[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_lo[lane][cc];
+    }
+    if (wy == 0) {
+      // column sums of the rounded centred values (the closed-form bandwidth term of the fused gradient needs
+      // sum_j z_j of exactly the operand the tensor core sees, not of the unrounded data)
+      float cs = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) cs += tile_hi[rr][lane] + (SPLIT3 ? tile_lo[rr][lane] : 0.f);
+      if (cs != 0.f) atomicAdd(colsum_hi + ct * 32 + lane, (double)cs);
     }
     __syncthreads();
   }
@@ -1592,10 +1601,10 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
   dim3 g2(rb, nsplit), b2(32, 8);
   if (L.split3)
     prep_center_kernel<true><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
-                                                 racc, a, acc);
+                                                 racc, a, acc, reinterpret_cast<double *>(ws + L.off_colsum_hi));
   else
     prep_center_kernel<false><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
-                                                  racc, a, acc);
+                                                  racc, a, acc, reinterpret_cast<double *>(ws + L.off_colsum_hi));
   EDRL_LAUNCHED();
   return 0;
 }
@@ -1700,15 +1709,18 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 }
 
 
-// dZ[i, f] = g sign(M) 4 (U[i, f] + c n z_i[f]) -- the closed-form bandwidth term on top of the fused pass
+// dZ[i, f] = g sign(M) 4 (U[i, f] + c (n z_i[f] - sum_j z_j[f])) -- the closed-form bandwidth term on top of the
+// fused pass, on the same rounded centred operand the sweep used (sum_j z_j is its column sum, ~0 but not 0)
 __global__ void __launch_bounds__(256)
-mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ stats,
+mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const double *__restrict__ colsum_hi,
+                      const float *__restrict__ stats,
                       const float *__restrict__ grad_out, int row_begin, int row_count, int row_begin2, int row_count2,
                       int d, int d_pad, int n, int nslab, float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
-  const float cn = stats[EDRL_MMD_STAT_C] * (float)n;
+  const float cv = stats[EDRL_MMD_STAT_C];
+  const float fn = (float)n;
   const size_t total = (size_t)(row_count + row_count2) * d;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / d;
@@ -1716,7 +1728,8 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
     const size_t gr = (r < (size_t)row_count) ? (size_t)row_begin + r : (size_t)row_begin2 + (r - row_count);
     float u = U[i];
     for (int sl = 1; sl < nslab; ++sl) u += U[(size_t)sl * total + i];       // partial slabs of the J-split sweep
-    dz[i] = coef * fmaf(cn, __ldg(zhi + gr * d_pad + f), u);
+    const float t = fmaf(fn, __ldg(zhi + gr * d_pad + f), -(float)colsum_hi[f]);
+    dz[i] = coef * fmaf(cv, t, u);
   }
 }
 
@@ -1903,7 +1916,8 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   const int cap = 8 * (device_sm_count() > 0 ? device_sm_count() : 148);
   if (blocks > cap) blocks = cap;
   mmd_apply_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      U, reinterpret_cast<const float *>(ws + L.off_zhi), stats, grad_out, row_begin, row_count, row_begin2, row_count2,
+      U, reinterpret_cast<const float *>(ws + L.off_zhi), reinterpret_cast<const double *>(ws + L.off_colsum_hi), stats,
+      grad_out, row_begin, row_count, row_begin2, row_count2,
       d, L.d_pad, L.n, edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2), dZ);
   EDRL_LAUNCHED();
   return 0;

@@ -360,3 +360,38 @@ def test_cuda_graph_capture_of_a_training_step():
         if first is None:
             first = l1.item()
     assert not np.isclose(first, l1.item(), rtol=1e-3)
+
+
+# ---------------------------------------------------------------- ragged shapes (tile / chunk / pass boundaries)
+RAGGED = [(1, 1, 1), (1, 7, 3), (2, 2, 65), (127, 1, 63), (129, 127, 64), (128, 128, 33), (255, 257, 512),
+          (100, 300, 513), (64, 64, 1025), (5, 9, 3072)]
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+@pytest.mark.parametrize("ns,nt,d", RAGGED)
+def test_ragged_shapes_vs_oracle(ns, nt, d, mode):
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    rng = np.random.default_rng(ns * 7919 + nt * 31 + d)
+    x = rng.standard_normal((ns, d)) * 0.7 - 0.1
+    y = rng.standard_normal((nt, d)) * 1.1 + 0.3
+    xt = dev(x).requires_grad_(True)
+    yt = dev(y).requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, precision=name)
+    loss.backward()
+    x32, y32 = xt.detach().cpu().numpy().astype(np.float64), yt.detach().cpu().numpy().astype(np.float64)
+    ref, _, dx, dy = O.mk_mmd_grad(x32, y32)
+    assert np.isclose(loss.item(), ref, rtol=ltol, atol=1e-6), (loss.item(), ref)
+    gmax = max(np.abs(dx).max(), np.abs(dy).max())
+    if ns + nt == 2:
+        # one sample per side: the loss is a constant (scale covariance), the true gradient is identically zero and
+        # what is left is rounding of the two cancelling terms -- bound it by the size of one term,
+        # 4 |G| |x - y| <= 4 * 5 / sigma_0 * |x - y|
+        _, st = edrl_b200.mk_mmd_with_stats(dev(x), dev(y), precision=name)
+        gmax = 20.0 / st[1].item() * np.abs(x32 - y32).max()
+    assert np.abs(xt.grad.cpu().numpy() - dx).max() <= gtol * gmax
+    assert np.abs(yt.grad.cpu().numpy() - dy).max() <= gtol * gmax
+    # loss-only evaluation (no gradient requested) takes the symmetric forward kernel
+    with torch.no_grad():
+        l0 = edrl_b200.MK_MMD(dev(x), dev(y), precision=name)
+    assert np.isclose(l0.item(), ref, rtol=ltol, atol=1e-6)
