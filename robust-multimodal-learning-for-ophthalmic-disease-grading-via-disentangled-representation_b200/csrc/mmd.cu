@@ -1709,6 +1709,399 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 }
 
 
+
+// ----------------------------------------------------------------------------- K3q: CTA-pair sweep, 256-column S tiles
+// Same decomposition as mmd_bwd_pair_kernel (S phase -> G -> transposed P phase over a 2-CTA cluster), but the S
+// phase works on TWO column tiles at once: tcgen05 M = 128 (64 rows of the panel per CTA), N = 256 (128 rows of Z_J
+// per CTA).  With 64 A rows per CTA the N = 128 S phase re-read 4 KiB of shared memory per 32-clk MMA (the whole
+// 128 B/clk port); N = 256 reads 6 KiB per 64 clk, the Z_I chunk is fetched once per 256 columns instead of per 128,
+// and the MMAs are twice as long (half the issue slots).  Z_I is streamed (two 32-column chunks per ring stage), the
+// ring has 9 stages of 16 KiB, G is 64 rows x 256 columns (64 KiB) per CTA.
+constexpr int Q_GROUP = 256;                   // columns per S group
+constexpr int Q_G_BYTES = 8 * P2_CHUNK;        // 64 rows x 256 columns j
+constexpr int Q_CTRL_BYTES = 5120;
+constexpr int Q_STAGES = 9;
+constexpr int Q_SMEM_BYTES = Q_G_BYTES + Q_STAGES * P2_STAGE + Q_CTRL_BYTES;
+
+struct SweepCtrl {
+  uint64_t full[12];              // leader CTA only
+  uint64_t empty[12];             // per CTA (multicast commit)
+  uint64_t s_full[2];             // per CTA (multicast commit)
+  uint64_t s_empty[2];            // leader, 16 arrivals
+  uint64_t g_full;                // leader, 16 arrivals
+  uint64_t g_empty;               // per CTA (multicast commit)
+  uint64_t dz_full;               // per CTA (multicast commit)
+  uint32_t tmem_base;
+  uint32_t pad;
+  float2 colinfo[2][Q_GROUP];     // (r_j, a_j) per S stage; re-used for the row-sum exchange after the sweep
+  float negc[MAX_KERNELS];
+  float w[MAX_KERNELS];
+  double red[8][2];
+};
+static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
+static_assert(Q_SMEM_BYTES <= 232448, "smem budget");
+
+template <bool FAST, bool FUSED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
+mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_z128,
+                    const __grid_constant__ CUtensorMap tm_zt, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *g_smem = smem;
+  uint8_t *ring = g_smem + Q_G_BYTES;
+  SweepCtrl *ctl = reinterpret_cast<SweepCtrl *>(ring + Q_STAGES * P2_STAGE);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int panel = blockIdx.x >> 1;
+  const int np1 = (p.row_count + BM - 1) / BM;
+  const bool second = panel >= np1;
+  const int lpanel = second ? panel - np1 : panel;
+  const int rng_begin = second ? p.row_begin2 : p.row_begin;
+  const int rng_count = second ? p.row_count2 : p.row_count;
+  const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;
+  const int row_base = rng_begin + lpanel * BM;
+  const int f0 = blockIdx.y * P2_FEATS;
+  const int nG = p.nb / 2;                                // groups of 256 columns (n_pad is a multiple of 256)
+  const int kchunks = p.kchunks;                          // even
+  const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;
+
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Q_STAGES; ++s) {
+      mbar_init(&ctl->full[s], 1);
+      mbar_init(&ctl->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl->s_full[s], 1);
+      mbar_init(&ctl->s_empty[s], 2 * BWD_EPI_THREADS / 32);
+    }
+    mbar_init(&ctl->g_full, 2 * BWD_EPI_THREADS / 32);
+    mbar_init(&ctl->g_empty, 1);
+    mbar_init(&ctl->dz_full, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&ctl->tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_z64);
+    tma_prefetch_desc(&tm_z128);
+    tma_prefetch_desc(&tm_zt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_dz = tmem_base;                     // columns [0, 256): two M-tiles of dZ^T
+  const uint32_t tmem_s = tmem_base + 256;                // two S stages of 128 columns (64 rows x 256)
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, warp-converged issue) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t full0 = mapa_u32(smem_u32(&ctl->full[0]), 0);
+    auto acquire = [&]() -> uint8_t * {
+      mbar_wait(&ctl->empty[s], ph ^ 1);
+      mbar_expect_tx_elect(&ctl->full[s], 2 * P2_STAGE, leader ? 1u : 0u);
+      return ring + s * P2_STAGE;
+    };
+    auto next = [&]() {
+      if (++s == Q_STAGES) {
+        s = 0;
+        ph ^= 1;
+      }
+    };
+    const int irow = row_base + (int)rank * 64;
+    auto load_S = [&](int g) {
+      const int jrow = g * Q_GROUP + (int)rank * 128;
+      for (int kc = 0; kc < kchunks; kc += 2) {
+        {                                                   // two chunks of this CTA's 64 panel rows
+          uint8_t *st = acquire();
+          const uint32_t bar = full0 + 8u * (uint32_t)s;
+          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * BK, irow);
+          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * BK, irow);
+          next();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
+          uint8_t *st = acquire();
+          const uint32_t bar = full0 + 8u * (uint32_t)s;
+          tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * BK, jrow);
+          next();
+        }
+      }
+    };
+    auto load_P = [&](int g) {
+      for (int t = 0; t < ntile; ++t)
+        for (int a8 = 0; a8 < Q_GROUP / BK; ++a8) {
+          uint8_t *st = acquire();
+          const uint32_t bar = full0 + 8u * (uint32_t)s;
+          tma_load_2d_pair_elect(st, &tm_zt, bar, g * Q_GROUP + a8 * BK, f0 + t * 256 + (int)rank * 128);
+          next();
+        }
+    };
+    load_S(0);
+    for (int g = 0; g < nG; ++g) {
+      if (g + 1 < nG) load_S(g + 1);
+      load_P(g);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, warp-converged issue) =====================
+    if (leader) {
+      constexpr uint32_t idesc_s = make_idesc_tf32(128, Q_GROUP);     // 64 panel rows / 128 column rows per CTA
+      constexpr uint32_t idesc_p = make_idesc_tf32(256, BN);          // 128 feature rows / 64 panel rows per CTA
+      int s = 0;
+      uint32_t ph = 0;
+      auto next = [&]() {
+        if (++s == Q_STAGES) {
+          s = 0;
+          ph ^= 1;
+        }
+      };
+      const uint32_t ring_addr = smem_u32(ring);
+      const uint32_t g_addr = smem_u32(g_smem);
+      auto issue_S = [&](int g) {
+        const int b = g & 1;
+        const uint32_t u = (uint32_t)(g >> 1);
+        mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_s + b * 128;
+        for (int kc = 0; kc < kchunks; kc += 2) {
+          mbar_wait(&ctl->full[s], ph);                    // the Z_I stage (two chunks)
+          tc_fence_after();
+          const int sa = s;
+          const uint32_t a_st = ring_addr + s * P2_STAGE;
+          next();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&ctl->full[s], ph);                  // the Z_J chunk
+            tc_fence_after();
+            const uint64_t a_d = make_kmajor_sw128_desc(a_st + h * P2_CHUNK);
+            const uint64_t b_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
+            }
+            if (h == 1) mma_commit_pair_elect(&ctl->empty[sa]);
+            mma_commit_pair_elect(&ctl->empty[s]);
+            next();
+          }
+        }
+        mma_commit_pair_elect(&ctl->s_full[b]);
+      };
+      auto issue_P = [&](int g) {
+        mbar_wait_cluster(&ctl->g_full, (uint32_t)(g & 1));
+        tc_fence_after();
+        for (int t = 0; t < ntile; ++t)
+          for (int a8 = 0; a8 < Q_GROUP / BK; ++a8) {
+            mbar_wait(&ctl->full[s], ph);
+            tc_fence_after();
+            const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+            const uint64_t b_d = make_kmajor_sw128_desc(g_addr + a8 * P2_CHUNK);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+              mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
+                                     (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit_pair_elect(&ctl->empty[s]);
+            next();
+          }
+        mma_commit_pair_elect(&ctl->g_empty);
+      };
+      issue_S(0);
+      for (int g = 0; g < nG; ++g) {
+        if (g + 1 < nG) issue_S(g + 1);
+        issue_P(g);
+      }
+      mma_commit_pair_elect(&ctl->dz_full);
+    }
+  } else {
+    // ===================== epilogue (both CTAs): S -> G for this CTA's 64 rows x 256 columns =====================
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int ch = ew >> 2;                  // which 64 of the S stage's 128 TMEM columns
+    const int et = ew * 32 + lane;
+    const int tl = lg * 32 + lane;           // TMEM lane
+    const int r = tl & 63;                   // row of this CTA's 64-row slice
+    const int jh = tl >> 6;                  // lanes 64..127 hold columns 128..255 of the same rows (2x2 layout)
+    const int gi = row_base + (int)rank * 64 + r;
+
+    const double sum_r = FUSED ? p.acc[2] : 0.0;
+    const float sigma0 = FUSED ? (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
+    const float cval = FUSED ? 0.f : p.stats[EDRL_MMD_STAT_C];
+    float sig_last = sigma0;
+    for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
+    const float negc_last = -LOG2E / sig_last;
+    if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
+
+    const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
+    const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
+    const float nai_sig = -ai / sigma0;
+    const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
+    float rowsum = 0.f;
+    const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
+    const float ai_m = count_row ? ai : 0.f;
+    double accM = 0.0, accD = 0.0;
+
+    for (int g = 0; g < nG; ++g) {
+      const int b = g & 1;
+      const uint32_t u = (uint32_t)(g >> 1);
+      {
+        const int gj = g * Q_GROUP + et;                  // 256 epilogue threads fill the 256 column entries
+        ctl->colinfo[b][et] = make_float2((float)p.racc[gj], p.a[gj]);
+      }
+      named_barrier_sync(1, BWD_EPI_THREADS);
+      mbar_wait(&ctl->s_full[b], u & 1);
+      tc_fence_after();
+      mbar_wait(&ctl->g_empty, (uint32_t)((g & 1) ^ 1));   // P(g-1) has consumed the G buffer
+      float tM = 0.f, tD = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int j0 = jh * 128 + ch * 64 + c * 32;        // first of these 32 columns inside the group
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + ch * 64 + c * 32), v);
+        tmem_ld_wait();
+        float gq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 ci = ctl->colinfo[b][j0 + j];
+          const float Lraw = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
+          const float L = fmaxf(Lraw, 0.f);
+          float K, Q;
+          kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+          if (FUSED) {
+            tM = fmaf(ci.y, K, tM);
+            tD = fmaf(ci.y * L, Q, tD);
+          }
+          float gv = FUSED ? (ci.y * Q) * nai_sig : fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);
+          gv = (Lraw >= 0.f) ? gv : 0.f;
+          const float gh = to_tf32(gv);
+          gq[j] = gh;
+          rowsum += gh;
+        }
+        uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<float4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
+              make_float4(gq[q4 * 4 + 0], gq[q4 * 4 + 1], gq[q4 * 4 + 2], gq[q4 * 4 + 3]);
+      }
+      if (FUSED) {
+        accM += (double)(ai_m * tM);
+        accD += (double)(ai_m * tD);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(g_full_leader);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->s_empty[b]), 0));
+      }
+    }
+    if (FUSED && blockIdx.y == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        accM += __shfl_xor_sync(0xffffffffu, accM, o);
+        accD += __shfl_xor_sync(0xffffffffu, accD, o);
+      }
+      if (lane == 0) {
+        ctl->red[ew][0] = accM;
+        ctl->red[ew][1] = accD;
+      }
+      named_barrier_sync(1, BWD_EPI_THREADS);
+      if (et == 0) {
+        double m = 0.0, dd = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          m += ctl->red[k][0];
+          dd += ctl->red[k][1];
+        }
+        atomicAdd(p.acc + 0, m);
+        atomicAdd(p.acc + 1, dd);
+        __threadfence();
+        const unsigned t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+          __threadfence();
+          const double Mv = atomicAdd(p.acc + 0, 0.0);
+          const double Ds = atomicAdd(p.acc + 1, 0.0);
+          if (p.partial) {
+            p.partial[0] = Mv;
+            p.partial[1] = Ds;
+          }
+          if (p.finalize) write_final_stats(Mv, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats_out);
+        }
+      }
+    }
+    // ---- row sums of G: 4 partials per row (2 lane halves x 2 column halves) -> all 128 rows in both CTAs ----
+    named_barrier_sync(1, BWD_EPI_THREADS);
+    float *part = reinterpret_cast<float *>(&ctl->colinfo[0][0]);   // [4][64]
+    float *rs_all = reinterpret_cast<float *>(&ctl->colinfo[1][0]); // [128]
+    part[(jh * 2 + ch) * 64 + r] = rowsum;
+    named_barrier_sync(1, BWD_EPI_THREADS);
+    if (et < 64) {
+      const float tot = (part[et] + part[64 + et]) + (part[128 + et] + part[192 + et]);
+      rs_all[rank * 64 + et] = tot;
+      st_cluster_f32(mapa_u32(smem_u32(&rs_all[rank * 64 + et]), rank ^ 1u), tot);
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();
+
+  if (warp >= 2) {
+    // ===================== write-out: dZ[i, f] = coef (rowsum_i z_i[f] - dZ^T[f, i]) =====================
+    const int ew = warp - 2;
+    const int lg = warp & 3;
+    const int ch = ew >> 2;
+    const int tl = lg * 32 + lane;
+    const float *rs_all = reinterpret_cast<const float *>(&ctl->colinfo[1][0]);
+    float coef = 1.f;
+    if (!FUSED) {
+      const float M = p.stats[EDRL_MMD_STAT_M];
+      const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
+      coef = 4.f * sgn * p.grad_out[0];
+    }
+    int rows_here = rng_count - lpanel * BM;
+    if (rows_here > BM) rows_here = BM;
+    if (p.n - row_base < rows_here) rows_here = p.n - row_base;
+    mbar_wait(&ctl->dz_full, 0);
+    tc_fence_after();
+    for (int t = 0; t < ntile; ++t) {
+      const int f = f0 + t * 256 + (int)rank * 128 + tl;
+      const bool f_ok = f < p.d;
+#pragma unroll 1
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int i0 = ch * 64 + c2 * 32;
+        if (i0 >= rows_here) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_dz + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BN + i0), v);
+        tmem_ld_wait();
+        if (f_ok) {
+          const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
+          float *oc = p.dz + (size_t)(out_row0 + i0) * p.d + f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (i0 + j < rows_here)
+              oc[(size_t)j * p.d] = coef * fmaf(rs_all[i0 + j], zc[(size_t)j * p.d_pad], -__uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // dZ[i, f] = g sign(M) 4 (U[i, f] + c (n z_i[f] - sum_j z_j[f])) -- the closed-form bandwidth term on top of the
 // fused pass, on the same rounded centred operand the sweep used (sum_j z_j is its column sum, ~0 but not 0)
 __global__ void __launch_bounds__(256)
@@ -1743,6 +2136,23 @@ static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt
   kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_z64, tm_zt, p);
   EDRL_LAUNCHED();
   return 0;
+}
+
+template <bool FAST, bool FUSED>
+static int launch_sweep256_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z128, const CUtensorMap &tm_zt,
+                             const BwdParams &p, dim3 grid, cudaStream_t st) {
+  auto kern = mmd_sweep256_kernel<FAST, FUSED>;
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+  kern<<<grid, BWD_THREADS, Q_SMEM_BYTES, st>>>(tm_z64, tm_z128, tm_zt, p);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
+static bool use_sweep256() {
+  // 256-column S tiles are the default for the fused sweep (1.16 -> 1.02 ms at N=8192, d=512);
+  // EDRL_MMD_SWEEP256=0 selects mmd_bwd_pair_kernel<.., FUSED> (128-column tiles, half-resident Z_I) for A/B runs
+  static const char *env = getenv("EDRL_MMD_SWEEP256");
+  return env == nullptr || atoi(env) != 0;
 }
 
 }  // namespace mmd
@@ -1895,6 +2305,12 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS,
              edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2));
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
+  if (use_sweep256() && grid2.z == 1) {
+    CUtensorMap tm_z128;
+    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (fast) return launch_sweep256_t<true, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+    return launch_sweep256_t<false, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+  }
   if (L.d_pad <= 512) {
     if (fast) return launch_bwd_pair_t<true, 8, true>(tm_z64, tm_zt, p, grid2, st);
     return launch_bwd_pair_t<false, 8, true>(tm_z64, tm_zt, p, grid2, st);
