@@ -624,9 +624,9 @@ def run_ours(args, rank, local_rank, world):
             g_ms = timed_steps(fused_only, reps, 2, flush, 1) / reps
             flops_g = flops_f + flops_b
             ach = flops_g / (g_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "mmd_bwd_pair_kernel<FUSED> (forward sums + gradient, one Gram sweep)",
+            roof = {"bound": "tensor", "kernel": "mmd_sweep256_kernel<FUSED> (forward sums + gradient, one Gram sweep)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": (profiled_traffic("mmd_bwd_pair_kernel<1, 8, 1>") if (N, d) == (8192, 512) else None),
+                    "traffic": (profiled_traffic("mmd_sweep256_kernel<1, 1>") if (N, d) == (8192, 512) else None),
                     "traffic_note": "DRAM bytes per launch (ncu, profiles/); algorithmic HBM bytes are 3 n d 4 = 96 MiB "
                                     "(read Z and Z^T, write U) -- the kernel is bound by L2 -> SM traffic, not DRAM",
                     "ms": g_ms,

@@ -2103,26 +2103,45 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
 }
 
 // dZ[i, f] = g sign(M) 4 (U[i, f] + c (n z_i[f] - sum_j z_j[f])) -- the closed-form bandwidth term on top of the
-// fused pass, on the same rounded centred operand the sweep used (sum_j z_j is its column sum, ~0 but not 0)
-__global__ void __launch_bounds__(256)
+// fused pass, on the same rounded centred operand the sweep used (sum_j z_j is its column sum, ~0 but not 0);
+// one block row per output row (no per-element division), 128-bit accesses when d % 4 == 0
+template <bool VEC4>
+__global__ void __launch_bounds__(128)
 mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const double *__restrict__ colsum_hi,
-                      const float *__restrict__ stats,
-                      const float *__restrict__ grad_out, int row_begin, int row_count, int row_begin2, int row_count2,
-                      int d, int d_pad, int n, int nslab, float *__restrict__ dz) {
+                      const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
+                      int row_begin2, int row_count2, int d, int d_pad, int n, int nslab, float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
   const float cv = stats[EDRL_MMD_STAT_C];
   const float fn = (float)n;
-  const size_t total = (size_t)(row_count + row_count2) * d;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / d;
-    const int f = (int)(i - r * d);
-    const size_t gr = (r < (size_t)row_count) ? (size_t)row_begin + r : (size_t)row_begin2 + (r - row_count);
-    float u = U[i];
-    for (int sl = 1; sl < nslab; ++sl) u += U[(size_t)sl * total + i];       // partial slabs of the J-split sweep
-    const float t = fmaf(fn, __ldg(zhi + gr * d_pad + f), -(float)colsum_hi[f]);
-    dz[i] = coef * fmaf(cv, t, u);
+  const int r = blockIdx.x;                                   // output row
+  const size_t gr = (r < row_count) ? (size_t)row_begin + r : (size_t)row_begin2 + (r - row_count);
+  const size_t slab = (size_t)(row_count + row_count2) * d;
+  const float *zr = zhi + gr * d_pad;
+  const float *ur = U + (size_t)r * d;
+  float *orow = dz + (size_t)r * d;
+  if (VEC4) {
+    for (int f = (blockIdx.y * 128 + threadIdx.x) * 4; f < d; f += gridDim.y * 512) {
+      float4 u = *reinterpret_cast<const float4 *>(ur + f);
+      for (int sl = 1; sl < nslab; ++sl) {
+        const float4 w = *reinterpret_cast<const float4 *>(ur + sl * slab + f);
+        u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
+      }
+      const float4 z = __ldg(reinterpret_cast<const float4 *>(zr + f));
+      float4 o;
+      o.x = coef * fmaf(cv, fmaf(fn, z.x, -(float)colsum_hi[f + 0]), u.x);
+      o.y = coef * fmaf(cv, fmaf(fn, z.y, -(float)colsum_hi[f + 1]), u.y);
+      o.z = coef * fmaf(cv, fmaf(fn, z.z, -(float)colsum_hi[f + 2]), u.z);
+      o.w = coef * fmaf(cv, fmaf(fn, z.w, -(float)colsum_hi[f + 3]), u.w);
+      *reinterpret_cast<float4 *>(orow + f) = o;
+    }
+  } else {
+    for (int f = blockIdx.y * 128 + threadIdx.x; f < d; f += gridDim.y * 128) {
+      float u = ur[f];
+      for (int sl = 1; sl < nslab; ++sl) u += ur[sl * slab + f];
+      dz[(size_t)r * d + f] = coef * fmaf(cv, fmaf(fn, __ldg(zr + f), -(float)colsum_hi[f]), u);
+    }
   }
 }
 
@@ -2327,14 +2346,19 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   EDRL_CHECK_ARG(workspace_bytes >= L.total, "MK_MMD apply_grad: workspace too small");
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n, "MK_MMD apply_grad: bad row range");
   const uint8_t *ws = reinterpret_cast<const uint8_t *>(workspace);
-  const size_t total = (size_t)(row_count + row_count2) * d;
-  int blocks = (int)((total + 255) / 256);
-  const int cap = 8 * (device_sm_count() > 0 ? device_sm_count() : 148);
-  if (blocks > cap) blocks = cap;
-  mmd_apply_grad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      U, reinterpret_cast<const float *>(ws + L.off_zhi), reinterpret_cast<const double *>(ws + L.off_colsum_hi), stats,
-      grad_out, row_begin, row_count, row_begin2, row_count2,
-      d, L.d_pad, L.n, edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2), dZ);
+  const int rows = row_count + row_count2;
+  const int nslab = edrl_mmd_grad_slabs(n_s, n_t, rows);
+  const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool v4 = (d % 4 == 0) && ((((uintptr_t)U | (uintptr_t)dZ) & 15) == 0);
+  dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
+  if (v4)
+    mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
+                                                      row_count2, d, L.d_pad, L.n, nslab, dZ);
+  else
+    mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
+                                                       row_count2, d, L.d_pad, L.n, nslab, dZ);
   EDRL_LAUNCHED();
   return 0;
 }

@@ -8,7 +8,7 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd|bwd)_pair_kernel" -s 8 -c 3 -o gpurun_out/prof_mmd_final -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"mmd_(fwd_pair|bwd_pair|sweep256)_kernel" -s 8 -c 3 -o gpurun_out/prof_mmd_final -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 python tools/run_topk.py > gpurun_out/plain_topk.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:topk_warp_radix -s 2 -c 2 -o gpurun_out/prof_topk_final -f python tools/run_topk.py > gpurun_out/ncu_topk.log 2>&1
