@@ -619,11 +619,14 @@ def run_ours(args, rank, local_rank, world):
                     "achieved": ach_f, "frac": ach_f / peak, "algorithmic_flops": flops_f}
         bwd_info = {"kernel": "mmd_bwd_pair_kernel (separate tile-recomputing backward)", "ms": b_ms,
                     "achieved": ach_b, "frac": ach_b / peak, "algorithmic_flops": flops_b}
-        if prec == "tf32":
+        if prec in ("tf32", "tf32h"):
             # the training step's dominant launch: forward sums + gradient in one sweep over the Gram tiles
             g_ms = timed_steps(fused_only, reps, 2, flush, 1) / reps
             flops_g = flops_f + flops_b
             ach = flops_g / (g_ms * 1e-3) / 1e12
+            if prec == "tf32h":
+                # Gram at the kind::tf32 rate, G.Z at the kind::f16 rate (twice as fast): blended peak for 1 : 2 work
+                peak = flops_g / (flops_f / peak + flops_b / (2.0 * peak))
             roof = {"bound": "tensor", "kernel": "mmd_sweep256_kernel<FUSED> (forward sums + gradient, one Gram sweep)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": (profiled_traffic("mmd_sweep256_kernel<1, 1>") if (N, d) == (8192, 512) else None),
@@ -631,7 +634,9 @@ def run_ours(args, rank, local_rank, world):
                                     "(read Z and Z^T, write U) -- the kernel is bound by L2 -> SM traffic, not DRAM",
                     "ms": g_ms,
                     "ms_includes": "the two prep kernels (~0.06 ms at N=8192) launched by the same C-ABI call",
-                    "peak_source": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)",
+                    "peak_source": (f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)" if prec == "tf32" else
+                                    f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s: Gram (1/3 of the work) at the "
+                                    "TF32 rate (/2), G.Z (2/3) at the f16 rate"),
                     "algorithmic_flops": flops_g, "mma_per_product": 1,
                     "executed_tensor_flops": (2.0 * n * n * d * passes + 2.0 * n * n * d)}
         else:
@@ -641,7 +646,7 @@ def run_ours(args, rank, local_rank, world):
                     "algorithmic_flops": flops_b, "mma_per_product": mma_per_product,
                     "executed_tensor_flops": (2.0 * n * n * d * math.ceil(d / 256) + 2.0 * n * n * d) * 3}
         if sharded:
-            one = (g_ms + 0.0) if prec == "tf32" else (f_ms + b_ms)
+            one = (g_ms + 0.0) if prec in ("tf32", "tf32h") else (f_ms + b_ms)
             base = {"n_gpus": 1, "ms_per_step": one, "value": N / (one * 1e-3),
                     "note": "same workload, unsharded, on rank 0 alone through the C-ABI (fused pass in TF32 mode; "
                             "the O(nd) apply_grad kernel is not included)"}
@@ -658,7 +663,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "tf32" if prec == "tf32" else "3xtf32", "data": "synthetic",
+            "dtype": prec, "data": "synthetic",
             "config": {"workload": wl["name"], "N_per_side": N, "d": d, "kernel_mul": 2.0, "kernel_num": 5,
                        "precision": prec, "parallelism": f"row-block x{world}" if sharded else "single GPU",
                        "l2": "256 MiB memset between steps (untimed); per-step CUDA events"},
@@ -682,18 +687,23 @@ def run_ours(args, rank, local_rank, world):
         if extras:
             line["essence_point"] = extras
             line["sweep_vs_torch_gpu"] = sweep_vs_torch_gpu(prec)
-            # the same step in the other precision mode (3xTF32 = hi/lo split, fp32-level accuracy: loss within 1e-6
-            # of the fp64 value; runs on the first-generation single-CTA kernels)
-            other = "3xtf32" if prec == "tf32" else "tf32"
+            # the same step in the other precision modes, same timing recipe
+            line["precision_modes"] = {prec: {"ms_per_step": ms_per_step, "value": value}}
+            for other in ("tf32", "tf32h", "3xtf32"):
+                if other == prec:
+                    continue
 
-            def other_step():
-                x.grad = None
-                y.grad = None
-                edrl_b200.MK_MMD(x, y, precision=other).backward()
+                def other_step(o=other):
+                    x.grad = None
+                    y.grad = None
+                    edrl_b200.MK_MMD(x, y, precision=o).backward()
 
-            line["precision_modes"] = {prec: {"ms_per_step": ms_per_step, "value": value},
-                                       other: (lambda t: {"ms_per_step": t, "value": N / (t * 1e-3)})(
-                                           timed_steps(other_step, 5, 3, flush, 1) / 5)}
+                t = timed_steps(other_step, 5, 3, flush, 1) / 5
+                line["precision_modes"][other] = {"ms_per_step": t, "value": N / (t * 1e-3)}
+            line["precision_modes"]["note"] = (
+                "tf32: TF32 Gram and TF32 G.Z (headline). tf32h: same TF32 Gram, G.Z operands stored as scaled "
+                "binary16 with the same 11-bit significands (gradients agree with tf32 to 2e-5 |g|_inf). 3xtf32: hi/lo "
+                "split, fp32-level accuracy, first-generation kernels.")
             line["essence_path_vs_torch_gpu"] = essence_path_vs_torch_gpu()
             line["eval_missing_modality"] = eval_missing_modality()
         print(json.dumps(line), flush=True)
@@ -708,7 +718,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32h", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()

@@ -35,6 +35,10 @@ extern "C" {
 /* flags for the MMD entry points */
 #define EDRL_MMD_TF32        0   /* Gram and G.Z on tcgen05 kind::tf32, operands rounded to TF32        */
 #define EDRL_MMD_3XTF32      1   /* hi/lo split operands, 3 MMAs per logical MMA (fp32-level accuracy)    */
+#define EDRL_MMD_TF32H       2   /* TF32 Gram; the G.Z product of the fused sweep reads its two operands as
+                                    power-of-two-scaled binary16 -- the SAME 11-bit significands as their TF32
+                                    roundings (the Z copy is bit-identical in value), half the bytes.  Only
+                                    edrl_mmd_forward_grad differs; every other entry point treats it as TF32.  */
 
 /* slots of the `stats` vector written by edrl_mmd_forward (8 floats) */
 #define EDRL_MMD_STAT_M       0  /* signed mean discrepancy  XX + YY - XY - YX          (code/MMD.py:66-69) */

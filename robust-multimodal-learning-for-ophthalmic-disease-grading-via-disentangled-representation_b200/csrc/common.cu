@@ -36,8 +36,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int make_tmap_2d(CUtensorMap *out, CUtensorMapDataType dt, const void *base, uint64_t rows, uint64_t cols,
+                        uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols);
+
 int make_tmap_2d_f32(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
                      uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rows, cols, row_pitch_bytes, box_rows, box_cols);
+}
+int make_tmap_2d_f16(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                     uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rows, cols, row_pitch_bytes, box_rows, box_cols);
+}
+
+static int make_tmap_2d(CUtensorMap *out, CUtensorMapDataType dt, const void *base, uint64_t rows, uint64_t cols,
+                        uint64_t row_pitch_bytes, uint32_t box_rows, uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
@@ -47,7 +59,7 @@ int make_tmap_2d_f32(CUtensorMap *out, const void *base, uint64_t rows, uint64_t
   cuuint64_t gstride[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+  CUresult r = enc(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -46,6 +46,10 @@ extern std::atomic<uint64_t> g_launches;
 int make_tmap_2d_f32(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
                      uint32_t box_rows, uint32_t box_cols);
 
+// same for binary16 elements (cols / box_cols in elements; 64 halfs = one 128-byte swizzle row)
+int make_tmap_2d_f16(CUtensorMap *out, const void *base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                     uint32_t box_rows, uint32_t box_cols);
+
 int device_sm_count();
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -23,6 +23,7 @@
 #include "../../include/edrl_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace edrl {
 namespace mmd {
@@ -40,8 +41,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 // ----------------------------------------------------------------------------- workspace
 struct Layout {
   int n, n_pad, d_pad;
-  bool split3;
-  size_t off_acc, off_colsum, off_colsum_hi, off_r, off_a, off_zhi, off_zthi, off_zlo, off_ztlo, total;
+  bool split3, h16;
+  size_t off_acc, off_colsum, off_colsum_hi, off_colmax, off_r, off_a, off_fscale, off_zhi, off_zthi, off_zlo, off_ztlo,
+      off_zt16, total;
   size_t zero_bytes;  // [off_acc, off_acc + zero_bytes) must be cleared before prep
 };
 
@@ -51,19 +53,23 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.n_pad = (int)align_up((size_t)L.n, 256);   // 256: the pair forward works on 256 x 256 tiles
   L.d_pad = (int)align_up((size_t)d, 64);   // 64: the pair kernels stage two 32-column chunks at a time
   L.split3 = (flags & EDRL_MMD_3XTF32) != 0;
+  L.h16 = !L.split3 && (flags & EDRL_MMD_TF32H) != 0;
   size_t o = 0;
   L.off_acc = o;      o += 256;                                   // 8 doubles + ticket counter
   L.off_colsum = o;   o += align_up((size_t)L.d_pad * 8, 256);    // double[d_pad]: column sums of [X; Y]
   L.off_colsum_hi = o; o += align_up((size_t)L.d_pad * 8, 256);   // double[d_pad]: column sums of the centred TF32 copy
+  L.off_colmax = o;   o += align_up((size_t)L.d_pad * 4, 256);    // uint32[d_pad]: bits of max |x| per column
   L.off_r = o;        o += align_up((size_t)L.n_pad * 8, 256);    // double[n_pad]
   L.zero_bytes = o - L.off_acc;
   L.off_a = o;        o += align_up((size_t)L.n_pad * 4, 256);    // float[n_pad]
+  L.off_fscale = o;   o += align_up((size_t)L.d_pad * 4, 256);    // int[d_pad]: binary16 scale exponent per column
   o = align_up(o, 1024);
   size_t zbytes = align_up((size_t)L.n_pad * L.d_pad * 4, 1024);
   L.off_zhi = o;      o += zbytes;
   L.off_zthi = o;     o += zbytes;
   L.off_zlo = o;      if (L.split3) o += zbytes;
   L.off_ztlo = o;     if (L.split3) o += zbytes;
+  L.off_zt16 = o;     if (L.h16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z^T [d_pad, n_pad]
   L.total = o;
   return L;
 }
@@ -71,28 +77,35 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
 // ----------------------------------------------------------------------------- K1: prep
 // column sums of Z = [X; Y] in double (for the mean)
 __global__ void __launch_bounds__(128) prep_colsum_kernel(const float *__restrict__ X, const float *__restrict__ Y,
-                                                          int n_s, int n, int d, double *__restrict__ colsum) {
+                                                          int n_s, int n, int d, double *__restrict__ colsum,
+                                                          unsigned *__restrict__ colmax) {
   const int col = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * 64;
   if (col >= d) return;
-  float acc = 0.f;
+  float acc = 0.f, mx = 0.f;
   const int r1 = min(r0 + 64, n);
 #pragma unroll 4
   for (int r = r0; r < r1; ++r) {
     const float *src = (r < n_s) ? (X + (size_t)r * d) : (Y + (size_t)(r - n_s) * d);
-    acc += __ldg(src + col);
+    const float v = __ldg(src + col);
+    acc += v;
+    mx = fmaxf(mx, fabsf(v));
   }
   atomicAdd(colsum + col, (double)acc);
+  if (colmax) atomicMax(colmax + col, __float_as_uint(mx));       // non-negative floats order like their bit patterns
 }
 
 // centre, round to tf32 (hi, optionally lo), write Z [n_pad, d_pad] and Z^T [d_pad, n_pad], row norms, weights
-template <bool SPLIT3>
+template <bool SPLIT3, bool H16 = false>
 __global__ void __launch_bounds__(256)
 prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int n_s, int n_t, int d, int n_pad,
                    int d_pad, const double *__restrict__ colsum, float *__restrict__ zhi, float *__restrict__ zthi,
                    float *__restrict__ zlo, float *__restrict__ ztlo, double *__restrict__ racc,
-                   float *__restrict__ a, double *__restrict__ acc, double *__restrict__ colsum_hi) {
+                   float *__restrict__ a, double *__restrict__ acc, double *__restrict__ colsum_hi,
+                   const unsigned *__restrict__ colmax = nullptr, int *__restrict__ fscale = nullptr,
+                   __half *__restrict__ zt16 = nullptr) {
   __shared__ float tile_hi[32][33];
+  __shared__ float s_scale[32];
   __shared__ float tile_lo[SPLIT3 ? 32 : 1][33];
   __shared__ float blk_sum[8];
   const int n = n_s + n_t;
@@ -103,6 +116,15 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
   for (int ct = blockIdx.y; ct < d_pad / 32; ct += gridDim.y) {
     const int col = ct * 32 + lane;
     const float mean = (col < d) ? (float)(colsum[col] * inv_n) : 0.f;
+    if (H16 && wy == 0) {
+      // binary16 copy of the column: scale by 2^e so that |z| < 2^14.  max |x - mean| <= max |x| + |mean|.
+      const float bnd = (col < d) ? (__uint_as_float(colmax[col]) + fabsf(mean)) : 0.f;
+      int ex = 0;
+      if (bnd > 0.f) frexpf(bnd, &ex);                 // bnd < 2^ex
+      const int e = (bnd > 0.f) ? 14 - ex : 0;
+      s_scale[lane] = ldexpf(1.f, e);
+      if (blockIdx.x == 0) fscale[col] = e;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int rr = wy * 4 + k;
@@ -130,6 +152,8 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
       const int cc = wy * 4 + k;
       zthi[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_hi[lane][cc];
       if (SPLIT3) ztlo[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_lo[lane][cc];
+      // the TF32 value has a 10-bit significand already: its scaled binary16 copy is exact (short of underflow)
+      if (H16) zt16[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = __float2half_rn(tile_hi[lane][cc] * s_scale[cc]);
     }
     if (wy == 0) {
       // column sums of the rounded centred values (the closed-form bandwidth term of the fused gradient needs
@@ -805,6 +829,7 @@ struct BwdParams {
   float *loss, *stats_out;         // written by the last CTA when finalize != 0
   int n_t, finalize;
   int row_begin2, row_count2;      // optional second row range (a rank's target rows); output rows follow range 1
+  const int *fscale;               // TF32H: binary16 scale exponent per feature column
 };
 
 // ring order (producer and MMA issuer walk the same sequence):
@@ -1592,7 +1617,8 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
   float *zlo = reinterpret_cast<float *>(ws + L.off_zlo);
   float *ztlo = reinterpret_cast<float *>(ws + L.off_ztlo);
   dim3 g1((d + 127) / 128, (n + 63) / 64);
-  prep_colsum_kernel<<<g1, 128, 0, st>>>(X, Y, n_s, n, d, colsum);
+  prep_colsum_kernel<<<g1, 128, 0, st>>>(X, Y, n_s, n, d, colsum,
+                                         L.h16 ? reinterpret_cast<unsigned *>(ws + L.off_colmax) : nullptr);
   EDRL_LAUNCHED();
   const int rb = L.n_pad / 32;
   int nsplit = (296 + rb - 1) / rb;
@@ -1602,6 +1628,11 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
   if (L.split3)
     prep_center_kernel<true><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
                                                  racc, a, acc, reinterpret_cast<double *>(ws + L.off_colsum_hi));
+  else if (L.h16)
+    prep_center_kernel<false, true><<<g2, b2, 0, st>>>(
+        X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo, racc, a, acc,
+        reinterpret_cast<double *>(ws + L.off_colsum_hi), reinterpret_cast<const unsigned *>(ws + L.off_colmax),
+        reinterpret_cast<int *>(ws + L.off_fscale), reinterpret_cast<__half *>(ws + L.off_zt16));
   else
     prep_center_kernel<false><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
                                                   racc, a, acc, reinterpret_cast<double *>(ws + L.off_colsum_hi));
@@ -1720,8 +1751,16 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 constexpr int Q_GROUP = 256;                   // columns per S group
 constexpr int Q_G_BYTES = 8 * P2_CHUNK;        // 64 rows x 256 columns j
 constexpr int Q_CTRL_BYTES = 5120;
-constexpr int Q_STAGES = 9;
-constexpr int Q_SMEM_BYTES = Q_G_BYTES + Q_STAGES * P2_STAGE + Q_CTRL_BYTES;
+// H16 (EDRL_MMD_TF32H): the P phase reads G and Z^T as scaled binary16 (kind::f16): G is 64 x 256 halfs = 32 KiB, a
+// Z^T stage holds 128 features x 64 columns, and the ring grows to 11 stages.
+template <bool H16>
+struct SweepCfg {
+  static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : Q_G_BYTES;
+  static constexpr int STAGES = H16 ? 11 : 9;
+  static constexpr int SMEM_BYTES = G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
+  static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : Q_GROUP / BK;     // K atoms (128-byte rows) per column group
+  static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
+};
 
 struct SweepCtrl {
   uint64_t full[12];              // leader CTA only
@@ -1739,15 +1778,17 @@ struct SweepCtrl {
   double red[8][2];
 };
 static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
-static_assert(Q_SMEM_BYTES <= 232448, "smem budget");
+static_assert(SweepCfg<false>::SMEM_BYTES <= 232448 && SweepCfg<true>::SMEM_BYTES <= 232448, "smem budget");
 
-template <bool FAST, bool FUSED>
+template <bool FAST, bool FUSED, bool H16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
 mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_z128,
                     const __grid_constant__ CUtensorMap tm_zt, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  using Cfg = SweepCfg<H16>;
+  constexpr int Q_STAGES = Cfg::STAGES;
   uint8_t *g_smem = smem;
-  uint8_t *ring = g_smem + Q_G_BYTES;
+  uint8_t *ring = g_smem + Cfg::G_BYTES;
   SweepCtrl *ctl = reinterpret_cast<SweepCtrl *>(ring + Q_STAGES * P2_STAGE);
 
   const int warp = threadIdx.x >> 5;
@@ -1838,10 +1879,10 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     };
     auto load_P = [&](int g) {
       for (int t = 0; t < ntile; ++t)
-        for (int a8 = 0; a8 < Q_GROUP / BK; ++a8) {
+        for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
           uint8_t *st = acquire();
           const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_zt, bar, g * Q_GROUP + a8 * BK, f0 + t * 256 + (int)rank * 128);
+          tma_load_2d_pair_elect(st, &tm_zt, bar, g * Q_GROUP + a8 * Cfg::P_ATOM_COLS, f0 + t * 256 + (int)rank * 128);
           next();
         }
     };
@@ -1854,7 +1895,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     // ===================== MMA issuer (leader CTA, warp-converged issue) =====================
     if (leader) {
       constexpr uint32_t idesc_s = make_idesc_tf32(128, Q_GROUP);     // 64 panel rows / 128 column rows per CTA
-      constexpr uint32_t idesc_p = make_idesc_tf32(256, BN);          // 128 feature rows / 64 panel rows per CTA
+      constexpr uint32_t idesc_p = H16 ? make_idesc_f16(256, BN) : make_idesc_tf32(256, BN);   // 128 features / 64 rows per CTA
       int s = 0;
       uint32_t ph = 0;
       auto next = [&]() {
@@ -1899,16 +1940,20 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         mbar_wait_cluster(&ctl->g_full, (uint32_t)(g & 1));
         tc_fence_after();
         for (int t = 0; t < ntile; ++t)
-          for (int a8 = 0; a8 < Q_GROUP / BK; ++a8) {
+          for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
             mbar_wait(&ctl->full[s], ph);
             tc_fence_after();
             const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
             const uint64_t b_d = make_kmajor_sw128_desc(g_addr + a8 * P2_CHUNK);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-              mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
-                                     (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
+              const uint64_t adv = (uint64_t)(k * 2);
+              if (H16)
+                mma_f16_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
+                                      (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+              else
+                mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
+                                       (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
             }
             mma_commit_pair_elect(&ctl->empty[s]);
             next();
@@ -1946,6 +1991,20 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const float nai_sig = -ai / sigma0;
     const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
     float rowsum = 0.f;
+    // H16: |G'| <= (sum_k mul^-k) / (sigma_0 min(n_s, n_t)^2); scale by 2^eg so that it stays below 2^14
+    float gs = 1.f, gs_inv = 1.f;
+    if (H16) {
+      float qmax = 0.f, wk = 1.f;
+      for (int k = 0; k < p.num; ++k) {
+        qmax += wk;
+        wk /= p.mul;
+      }
+      const float nmin = (float)min(p.n_s, p.n_t);
+      int ex = 0;
+      frexpf(qmax / (sigma0 * nmin * nmin), &ex);
+      gs = ldexpf(1.f, 14 - ex);
+      gs_inv = ldexpf(1.f, ex - 14);
+    }
     const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
     const float ai_m = count_row ? ai : 0.f;
     double accM = 0.0, accD = 0.0;
@@ -1982,15 +2041,40 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           }
           float gv = FUSED ? (ci.y * Q) * nai_sig : fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);
           gv = (Lraw >= 0.f) ? gv : 0.f;
-          const float gh = to_tf32(gv);
-          gq[j] = gh;
-          rowsum += gh;
+          if (H16) {
+            const float gh = __half2float(__float2half_rn(gv * gs));   // the value the tensor core will see
+            gq[j] = gh;
+            rowsum = fmaf(gh, gs_inv, rowsum);
+          } else {
+            const float gh = to_tf32(gv);
+            gq[j] = gh;
+            rowsum += gh;
+          }
         }
-        uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+        if (H16) {
+          // 32 halfs = 64 bytes = four 16-byte chunks of row r in K-atom (j0 / 64), 128-byte swizzle
+          uint8_t *atom = g_smem + (j0 >> 6) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+          const int cb = (j0 & 63) >> 3;
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          *reinterpret_cast<float4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
-              make_float4(gq[q4 * 4 + 0], gq[q4 * 4 + 1], gq[q4 * 4 + 2], gq[q4 * 4 + 3]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const __half2 h0 = __floats2half2_rn(gq[q4 * 8 + 0], gq[q4 * 8 + 1]);
+            const __half2 h1 = __floats2half2_rn(gq[q4 * 8 + 2], gq[q4 * 8 + 3]);
+            const __half2 h2 = __floats2half2_rn(gq[q4 * 8 + 4], gq[q4 * 8 + 5]);
+            const __half2 h3 = __floats2half2_rn(gq[q4 * 8 + 6], gq[q4 * 8 + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+            pk.z = *reinterpret_cast<const uint32_t *>(&h2);
+            pk.w = *reinterpret_cast<const uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) = pk;
+          }
+        } else {
+          uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            *reinterpret_cast<float4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
+                make_float4(gq[q4 * 4 + 0], gq[q4 * 4 + 1], gq[q4 * 4 + 2], gq[q4 * 4 + 3]);
+        }
       }
       if (FUSED) {
         accM += (double)(ai_m * tM);
@@ -2071,9 +2155,23 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     if (p.n - row_base < rows_here) rows_here = p.n - row_base;
     mbar_wait(&ctl->dz_full, 0);
     tc_fence_after();
+    float gs_inv = 1.f;                                       // H16: undo the scale of G (same formula as above)
+    if (H16) {
+      const float sigma0 = FUSED ? (float)bandwidth_sigma0(p.acc[2], p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
+      float qmax = 0.f, wk = 1.f;
+      for (int k = 0; k < p.num; ++k) {
+        qmax += wk;
+        wk /= p.mul;
+      }
+      const float nmin = (float)min(p.n_s, p.n_t);
+      int ex = 0;
+      frexpf(qmax / (sigma0 * nmin * nmin), &ex);
+      gs_inv = ldexpf(1.f, ex - 14);
+    }
     for (int t = 0; t < ntile; ++t) {
       const int f = f0 + t * 256 + (int)rank * 128 + tl;
       const bool f_ok = f < p.d;
+      const float unscale = (H16 && f_ok) ? ldexpf(gs_inv, -p.fscale[f]) : 1.f;     // and of column f of Z^T
 #pragma unroll 1
       for (int c2 = 0; c2 < 2; ++c2) {
         const int i0 = ch * 64 + c2 * 32;
@@ -2087,7 +2185,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (i0 + j < rows_here)
-              oc[(size_t)j * p.d] = coef * fmaf(rs_all[i0 + j], zc[(size_t)j * p.d_pad], -__uint_as_float(v[j]));
+              oc[(size_t)j * p.d] =
+                  coef * fmaf(rs_all[i0 + j], zc[(size_t)j * p.d_pad], -(__uint_as_float(v[j]) * unscale));
           }
         }
       }
@@ -2157,12 +2256,13 @@ static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt
   return 0;
 }
 
-template <bool FAST, bool FUSED>
+template <bool FAST, bool FUSED, bool H16 = false>
 static int launch_sweep256_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z128, const CUtensorMap &tm_zt,
                              const BwdParams &p, dim3 grid, cudaStream_t st) {
-  auto kern = mmd_sweep256_kernel<FAST, FUSED>;
-  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
-  kern<<<grid, BWD_THREADS, Q_SMEM_BYTES, st>>>(tm_z64, tm_z128, tm_zt, p);
+  auto kern = mmd_sweep256_kernel<FAST, FUSED, H16>;
+  constexpr int SMEM = SweepCfg<H16>::SMEM_BYTES;
+  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  kern<<<grid, BWD_THREADS, SMEM, st>>>(tm_z64, tm_z128, tm_zt, p);
   EDRL_LAUNCHED();
   return 0;
 }
@@ -2245,7 +2345,7 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   p.zlo = reinterpret_cast<const float *>(ws + L.off_zlo);
   p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
   p.acc = nullptr; p.ticket = nullptr; p.partial = nullptr; p.loss = nullptr; p.stats_out = nullptr;
-  p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0;
+  p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0; p.fscale = nullptr;
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
   if (!L.split3 && !legacy) {
@@ -2293,7 +2393,7 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
                           float *loss, float *stats, double *partial, float *U, void *workspace,
                           size_t workspace_bytes, void *stream) {
   EDRL_CHECK_ARG(X && Y && U, "MK_MMD forward_grad: null argument");
-  EDRL_CHECK_ARG((flags & EDRL_MMD_3XTF32) == 0, "MK_MMD forward_grad: the fused pass is TF32 only");
+  EDRL_CHECK_ARG((flags & EDRL_MMD_3XTF32) == 0, "MK_MMD forward_grad: the fused pass is TF32 / TF32H only");
   Layout L = make_layout(n_s, n_t, d, flags);
   if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n,
@@ -2324,6 +2424,16 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS,
              edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2));
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
+  p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
+  if (L.h16) {
+    // TF32 Gram, binary16 (scaled) operands for G.Z
+    CUtensorMap tm_z128, tm_zt16;
+    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (int rc = make_tmap_2d_f16(&tm_zt16, ws + L.off_zt16, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 2, 128, 64)) return rc;
+    grid2.z = 1;
+    if (fast) return launch_sweep256_t<true, true, true>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    return launch_sweep256_t<false, true, true>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+  }
   if (use_sweep256() && grid2.z == 1) {
     CUtensorMap tm_z128;
     if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;

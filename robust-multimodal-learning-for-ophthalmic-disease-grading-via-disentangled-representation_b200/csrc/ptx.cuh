@@ -254,6 +254,19 @@ __device__ __forceinline__ void mma_tf32_ss_elect(uint32_t d_tmem, uint64_t a_de
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (binary16 operands, fp32 accumulate) over a CTA pair, warp-converged issue
+__device__ __forceinline__ void mma_f16_ss_pair_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_pair_elect(uint64_t *bar) {
   asm volatile(
       "{\n\t"
@@ -330,6 +343,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 //   bit 15 / 16 A / B major (0 = K)  bits [17,23) N >> 3              bits [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with binary16 operands (A/B format 0 = F16), fp32 accumulate, K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- misc math
