@@ -39,6 +39,11 @@ extern "C" {
                                     power-of-two-scaled binary16 -- the SAME 11-bit significands as their TF32
                                     roundings (the Z copy is bit-identical in value), half the bytes.  Only
                                     edrl_mmd_forward_grad differs; every other entry point treats it as TF32.  */
+#define EDRL_MMD_F16S        4   /* TF32H, and the Gram of the fused sweep also reads a binary16 copy of the TF32-rounded
+                                    centred operand, scaled by one power of two for the whole matrix (same 11-bit
+                                    significands, exact products, fp32 accumulation): both contractions run at the
+                                    kind::f16 rate with half the shared-memory bytes.  Differs from TF32 only where a
+                                    value underflows binary16 (|z| < 2^-39 max|z|).  edrl_mmd_forward_grad only.      */
 
 /* slots of the `stats` vector written by edrl_mmd_forward (8 floats) */
 #define EDRL_MMD_STAT_M       0  /* signed mean discrepancy  XX + YY - XY - YX          (code/MMD.py:66-69) */

@@ -41,9 +41,9 @@ constexpr float LOG2E = 1.4426950408889634f;
 // ----------------------------------------------------------------------------- workspace
 struct Layout {
   int n, n_pad, d_pad;
-  bool split3, h16;
+  bool split3, h16, s16;
   size_t off_acc, off_colsum, off_colsum_hi, off_colmax, off_r, off_a, off_fscale, off_zhi, off_zthi, off_zlo, off_ztlo,
-      off_zt16, total;
+      off_zt16, off_z16, total;
   size_t zero_bytes;  // [off_acc, off_acc + zero_bytes) must be cleared before prep
 };
 
@@ -51,9 +51,11 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   Layout L;
   L.n = n_s + n_t;
   L.n_pad = (int)align_up((size_t)L.n, 256);   // 256: the pair forward works on 256 x 256 tiles
-  L.d_pad = (int)align_up((size_t)d, 64);   // 64: the pair kernels stage two 32-column chunks at a time
   L.split3 = (flags & EDRL_MMD_3XTF32) != 0;
-  L.h16 = !L.split3 && (flags & EDRL_MMD_TF32H) != 0;
+  L.s16 = !L.split3 && (flags & EDRL_MMD_F16S) != 0;
+  L.h16 = !L.split3 && (flags & (EDRL_MMD_TF32H | EDRL_MMD_F16S)) != 0;
+  // 64: the pair kernels stage two 32-column chunks at a time (F16S: two 64-column binary16 chunks)
+  L.d_pad = (int)align_up((size_t)d, L.s16 ? 128 : 64);
   size_t o = 0;
   L.off_acc = o;      o += 256;                                   // 8 doubles + ticket counter
   L.off_colsum = o;   o += align_up((size_t)L.d_pad * 8, 256);    // double[d_pad]: column sums of [X; Y]
@@ -62,7 +64,7 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.off_r = o;        o += align_up((size_t)L.n_pad * 8, 256);    // double[n_pad]
   L.zero_bytes = o - L.off_acc;
   L.off_a = o;        o += align_up((size_t)L.n_pad * 4, 256);    // float[n_pad]
-  L.off_fscale = o;   o += align_up((size_t)L.d_pad * 4, 256);    // int[d_pad]: binary16 scale exponent per column
+  L.off_fscale = o;   o += align_up((size_t)(L.d_pad + 1) * 4, 256);   // int[d_pad]: binary16 scale exponent per column; [d_pad]: of Z16
   o = align_up(o, 1024);
   size_t zbytes = align_up((size_t)L.n_pad * L.d_pad * 4, 1024);
   L.off_zhi = o;      o += zbytes;
@@ -70,6 +72,7 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.off_zlo = o;      if (L.split3) o += zbytes;
   L.off_ztlo = o;     if (L.split3) o += zbytes;
   L.off_zt16 = o;     if (L.h16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z^T [d_pad, n_pad]
+  L.off_z16 = o;      if (L.s16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z [n_pad, d_pad]
   L.total = o;
   return L;
 }
@@ -103,9 +106,10 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
                    float *__restrict__ zlo, float *__restrict__ ztlo, double *__restrict__ racc,
                    float *__restrict__ a, double *__restrict__ acc, double *__restrict__ colsum_hi,
                    const unsigned *__restrict__ colmax = nullptr, int *__restrict__ fscale = nullptr,
-                   __half *__restrict__ zt16 = nullptr) {
+                   __half *__restrict__ zt16 = nullptr, __half *__restrict__ z16 = nullptr) {
   __shared__ float tile_hi[32][33];
   __shared__ float s_scale[32];
+  __shared__ float s_gmax[8];
   __shared__ float tile_lo[SPLIT3 ? 32 : 1][33];
   __shared__ float blk_sum[8];
   const int n = n_s + n_t;
@@ -113,6 +117,26 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
   const int row0 = blockIdx.x * 32;
   const double inv_n = 1.0 / (double)n;
   float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  float gscale = 1.f;
+  if (H16 && z16) {
+    // F16S: the Gram operand Z16 = Z 2^e with ONE exponent for the whole matrix (a per-row or per-column scale would
+    // not factor out of z_i . z_j): |z| <= max_c (max |x_c| + |mean_c|) < 2^ex, e = 15 - ex
+    float b = 0.f;
+    for (int c = wy * 32 + lane; c < d; c += 256)
+      b = fmaxf(b, __uint_as_float(colmax[c]) + fabsf((float)(colsum[c] * inv_n)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if (lane == 0) s_gmax[wy] = b;
+    __syncthreads();
+    b = s_gmax[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) b = fmaxf(b, s_gmax[k]);
+    int ex = 0;
+    if (b > 0.f) frexpf(b, &ex);
+    const int e = (b > 0.f) ? 15 - ex : 0;
+    gscale = ldexpf(1.f, e);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && wy == 0 && lane == 0) fscale[d_pad] = e;
+  }
   for (int ct = blockIdx.y; ct < d_pad / 32; ct += gridDim.y) {
     const int col = ct * 32 + lane;
     const float mean = (col < d) ? (float)(colsum[col] * inv_n) : 0.f;
@@ -136,6 +160,7 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
       }
       const float hi = to_tf32(v);
       zhi[(size_t)row * d_pad + col] = hi;
+      if (H16 && z16) z16[(size_t)row * d_pad + col] = __float2half_rn(hi * gscale);   // exact unless it underflows
       tile_hi[rr][lane] = hi;
       if (SPLIT3) {
         const float lo = to_tf32(v - hi);
@@ -1632,7 +1657,8 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
     prep_center_kernel<false, true><<<g2, b2, 0, st>>>(
         X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo, racc, a, acc,
         reinterpret_cast<double *>(ws + L.off_colsum_hi), reinterpret_cast<const unsigned *>(ws + L.off_colmax),
-        reinterpret_cast<int *>(ws + L.off_fscale), reinterpret_cast<__half *>(ws + L.off_zt16));
+        reinterpret_cast<int *>(ws + L.off_fscale), reinterpret_cast<__half *>(ws + L.off_zt16),
+        L.s16 ? reinterpret_cast<__half *>(ws + L.off_z16) : nullptr);
   else
     prep_center_kernel<false><<<g2, b2, 0, st>>>(X, Y, n_s, n_t, d, L.n_pad, L.d_pad, colsum, zhi, zthi, zlo, ztlo,
                                                   racc, a, acc, reinterpret_cast<double *>(ws + L.off_colsum_hi));
@@ -1750,14 +1776,23 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 // ring has 9 stages of 16 KiB, G is 64 rows x 256 columns (64 KiB) per CTA.
 constexpr int Q_GROUP = 256;                   // columns per S group
 constexpr int Q_G_BYTES = 8 * P2_CHUNK;        // 64 rows x 256 columns j
-constexpr int Q_CTRL_BYTES = 5120;
-// H16 (EDRL_MMD_TF32H): the P phase reads G and Z^T as scaled binary16 (kind::f16): G is 64 x 256 halfs = 32 KiB, a
-// Z^T stage holds 128 features x 64 columns, and the ring grows to 11 stages.
-template <bool H16>
+constexpr int Q_CTRL_BYTES = 6144;
+constexpr int SW_EPI_WARPS = 16;               // 4 per TMEM lane group: one 32-column chunk of the S stage each
+constexpr int SW_EPI_THREADS = SW_EPI_WARPS * 32;
+constexpr int SW_THREADS = 64 + SW_EPI_THREADS;
+
+// MODE 0: TF32 everywhere.  1 (EDRL_MMD_TF32H): binary16 P phase.  2 (EDRL_MMD_F16S): the S phase too reads scaled
+// binary16 operands (Z16, kind::f16): a ring stage then holds 64 feature columns instead of 32.
+// The binary16 modes keep TWO G buffers (32 KiB each), so the epilogue of group g+1 overlaps the P phase of group g.
+template <int MODE>
 struct SweepCfg {
-  static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : Q_G_BYTES;
-  static constexpr int STAGES = H16 ? 11 : 9;
-  static constexpr int SMEM_BYTES = G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
+  static constexpr bool H16 = MODE >= 1;
+  static constexpr bool S16 = MODE == 2;
+  static constexpr int S_COLS = S16 ? 64 : BK;                         // feature columns per 128-byte row of an S operand
+  static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : Q_G_BYTES;      // one G buffer: 64 rows x 256 columns
+  static constexpr int G_BUFS = H16 ? 2 : 1;
+  static constexpr int STAGES = 9;
+  static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
   static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : Q_GROUP / BK;     // K atoms (128-byte rows) per column group
   static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
 };
@@ -1766,29 +1801,34 @@ struct SweepCtrl {
   uint64_t full[12];              // leader CTA only
   uint64_t empty[12];             // per CTA (multicast commit)
   uint64_t s_full[2];             // per CTA (multicast commit)
-  uint64_t s_empty[2];            // leader, 16 arrivals
-  uint64_t g_full;                // leader, 16 arrivals
-  uint64_t g_empty;               // per CTA (multicast commit)
+  uint64_t s_empty[2];            // leader, one arrival per epilogue warp of the pair
+  uint64_t g_full[2];             // leader, one arrival per epilogue warp of the pair
+  uint64_t g_empty[2];            // per CTA (multicast commit)
   uint64_t dz_full;               // per CTA (multicast commit)
   uint32_t tmem_base;
   uint32_t pad;
-  float2 colinfo[2][Q_GROUP];     // (r_j, a_j) per S stage; re-used for the row-sum exchange after the sweep
+  float col_r[2][Q_GROUP];        // r_j per S stage; re-used for the row-sum exchange after the sweep
+  float col_a[2][Q_GROUP];        // a_j per S stage
   float negc[MAX_KERNELS];
   float w[MAX_KERNELS];
-  double red[8][2];
+  double red[SW_EPI_WARPS][2];
+  float rs_all[BM];               // row sums of G for the panel's 128 rows (both CTAs hold all of them)
 };
 static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
-static_assert(SweepCfg<false>::SMEM_BYTES <= 232448 && SweepCfg<true>::SMEM_BYTES <= 232448, "smem budget");
+static_assert(SweepCfg<0>::SMEM_BYTES <= 232448 && SweepCfg<1>::SMEM_BYTES <= 232448, "smem budget");
 
-template <bool FAST, bool FUSED, bool H16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
+template <bool FAST, bool FUSED, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_THREADS, 1)
 mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_z128,
                     const __grid_constant__ CUtensorMap tm_zt, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  using Cfg = SweepCfg<H16>;
+  using Cfg = SweepCfg<MODE>;
+  constexpr bool H16 = Cfg::H16;
+  constexpr bool S16 = Cfg::S16;
   constexpr int Q_STAGES = Cfg::STAGES;
+  constexpr int GB = Cfg::G_BUFS;
   uint8_t *g_smem = smem;
-  uint8_t *ring = g_smem + Cfg::G_BYTES;
+  uint8_t *ring = g_smem + GB * Cfg::G_BYTES;
   SweepCtrl *ctl = reinterpret_cast<SweepCtrl *>(ring + Q_STAGES * P2_STAGE);
 
   const int warp = threadIdx.x >> 5;
@@ -1805,7 +1845,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int row_base = rng_begin + lpanel * BM;
   const int f0 = blockIdx.y * P2_FEATS;
   const int nG = p.nb / 2;                                // groups of 256 columns (n_pad is a multiple of 256)
-  const int kchunks = p.kchunks;                          // even
+  const int kchunks = S16 ? p.d_pad / 64 : p.kchunks;     // 128-byte K chunks of an S operand row; even
   const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -1816,10 +1856,10 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl->s_full[s], 1);
-      mbar_init(&ctl->s_empty[s], 2 * BWD_EPI_THREADS / 32);
+      mbar_init(&ctl->s_empty[s], 2 * SW_EPI_WARPS);
+      mbar_init(&ctl->g_full[s], 2 * SW_EPI_WARPS);
+      mbar_init(&ctl->g_empty[s], 1);
     }
-    mbar_init(&ctl->g_full, 2 * BWD_EPI_THREADS / 32);
-    mbar_init(&ctl->g_empty, 1);
     mbar_init(&ctl->dz_full, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -1864,15 +1904,15 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         {                                                   // two chunks of this CTA's 64 panel rows
           uint8_t *st = acquire();
           const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * BK, irow);
-          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * BK, irow);
+          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * Cfg::S_COLS, irow);
+          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * Cfg::S_COLS, irow);
           next();
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
           uint8_t *st = acquire();
           const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * BK, jrow);
+          tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * Cfg::S_COLS, jrow);
           next();
         }
       }
@@ -1894,7 +1934,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, warp-converged issue) =====================
     if (leader) {
-      constexpr uint32_t idesc_s = make_idesc_tf32(128, Q_GROUP);     // 64 panel rows / 128 column rows per CTA
+      constexpr uint32_t idesc_s = S16 ? make_idesc_f16(128, Q_GROUP) : make_idesc_tf32(128, Q_GROUP);   // 64 panel rows / 128 column rows per CTA
       constexpr uint32_t idesc_p = H16 ? make_idesc_f16(256, BN) : make_idesc_tf32(256, BN);   // 128 features / 64 rows per CTA
       int s = 0;
       uint32_t ph = 0;
@@ -1925,9 +1965,12 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
             const uint64_t a_d = make_kmajor_sw128_desc(a_st + h * P2_CHUNK);
             const uint64_t b_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-              mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
+              const uint64_t adv = (uint64_t)(k * 2);
+              if (S16)
+                mma_f16_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
+              else
+                mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
             }
             if (h == 1) mma_commit_pair_elect(&ctl->empty[sa]);
             mma_commit_pair_elect(&ctl->empty[s]);
@@ -1937,14 +1980,16 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         mma_commit_pair_elect(&ctl->s_full[b]);
       };
       auto issue_P = [&](int g) {
-        mbar_wait_cluster(&ctl->g_full, (uint32_t)(g & 1));
+        const int gb = g % GB;
+        const uint32_t gu = (uint32_t)(g / GB);
+        mbar_wait_cluster(&ctl->g_full[gb], gu & 1);
         tc_fence_after();
         for (int t = 0; t < ntile; ++t)
           for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
             mbar_wait(&ctl->full[s], ph);
             tc_fence_after();
             const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-            const uint64_t b_d = make_kmajor_sw128_desc(g_addr + a8 * P2_CHUNK);
+            const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + a8 * P2_CHUNK);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
               const uint64_t adv = (uint64_t)(k * 2);
@@ -1958,7 +2003,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
             mma_commit_pair_elect(&ctl->empty[s]);
             next();
           }
-        mma_commit_pair_elect(&ctl->g_empty);
+        mma_commit_pair_elect(&ctl->g_empty[gb]);
       };
       issue_S(0);
       for (int g = 0; g < nG; ++g) {
@@ -1969,13 +2014,16 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     }
   } else {
     // ===================== epilogue (both CTAs): S -> G for this CTA's 64 rows x 256 columns =====================
+    // 16 warps: warp % 4 fixes the TMEM lane group, cq = which 32 of the S stage's 128 TMEM columns.  A thread owns one
+    // row and 32 columns per group; the element math runs on packed fp32 pairs (FFMA2 / FMUL2 / FADD2).
     const int ew = warp - 2;
     const int lg = warp & 3;
-    const int ch = ew >> 2;                  // which 64 of the S stage's 128 TMEM columns
+    const int cq = ew >> 2;
     const int et = ew * 32 + lane;
     const int tl = lg * 32 + lane;           // TMEM lane
     const int r = tl & 63;                   // row of this CTA's 64-row slice
     const int jh = tl >> 6;                  // lanes 64..127 hold columns 128..255 of the same rows (2x2 layout)
+    const int j0 = jh * 128 + cq * 32;       // first of this thread's 32 columns inside a group
     const int gi = row_base + (int)rank * 64 + r;
 
     const double sum_r = FUSED ? p.acc[2] : 0.0;
@@ -1988,9 +2036,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
 
     const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
     const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
-    const float nai_sig = -ai / sigma0;
-    const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
-    float rowsum = 0.f;
+    const uint32_t s_empty_leader0 = mapa_u32(smem_u32(&ctl->s_empty[0]), 0);
+    const uint32_t g_full_leader0 = mapa_u32(smem_u32(&ctl->g_full[0]), 0);
     // H16: |G'| <= (sum_k mul^-k) / (sigma_0 min(n_s, n_t)^2); scale by 2^eg so that it stays below 2^14
     float gs = 1.f, gs_inv = 1.f;
     if (H16) {
@@ -2005,88 +2052,150 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       gs = ldexpf(1.f, 14 - ex);
       gs_inv = ldexpf(1.f, ex - 14);
     }
+    const float rc = (-ai / sigma0) * gs;                   // G'_ij 2^eg = (a_j Q_ij) rc
     const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
     const float ai_m = count_row ? ai : 0.f;
     double accM = 0.0, accD = 0.0;
+    // S16: the tensor core saw Z 2^e on both sides: S = 2^(2e) z_i . z_j
+    const float m2s = S16 ? -ldexpf(2.f, -2 * p.fscale[p.d_pad]) : -2.f;
+    float rowsum = 0.f;                                     // of the rounded G values, in units of 2^-eg
+
+    // (r_j, a_j) of the next group: fetched one group ahead by the first 256 epilogue threads
+    float nxt_r = 0.f, nxt_a = 0.f;
+    if (et < Q_GROUP) {
+      nxt_r = (float)p.racc[et];
+      nxt_a = p.a[et];
+    }
 
     for (int g = 0; g < nG; ++g) {
       const int b = g & 1;
       const uint32_t u = (uint32_t)(g >> 1);
-      {
-        const int gj = g * Q_GROUP + et;                  // 256 epilogue threads fill the 256 column entries
-        ctl->colinfo[b][et] = make_float2((float)p.racc[gj], p.a[gj]);
+      const int gb = g % GB;
+      const uint32_t gu = (uint32_t)(g / GB);
+      if (et < Q_GROUP) {
+        ctl->col_r[b][et] = nxt_r;
+        ctl->col_a[b][et] = nxt_a;
+        if (g + 1 < nG) {
+          nxt_r = (float)p.racc[(g + 1) * Q_GROUP + et];
+          nxt_a = p.a[(g + 1) * Q_GROUP + et];
+        }
       }
-      named_barrier_sync(1, BWD_EPI_THREADS);
+      named_barrier_sync(1, SW_EPI_THREADS);
       mbar_wait(&ctl->s_full[b], u & 1);
       tc_fence_after();
-      mbar_wait(&ctl->g_empty, (uint32_t)((g & 1) ^ 1));   // P(g-1) has consumed the G buffer
-      float tM = 0.f, tD = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int j0 = jh * 128 + ch * 64 + c * 32;        // first of these 32 columns inside the group
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + ch * 64 + c * 32), v);
-        tmem_ld_wait();
-        float gq[32];
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + cq * 32), v);
+      tmem_ld_wait();
+      // the S stage is free as soon as its values sit in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(s_empty_leader0 + 8u * (uint32_t)b);
+      uint32_t gp[H16 ? 16 : 32];                            // packed binary16 pairs / TF32 words of this row's G
+      const float4 *cr4 = reinterpret_cast<const float4 *>(&ctl->col_r[b][j0]);
+      const float4 *ca4 = reinterpret_cast<const float4 *>(&ctl->col_a[b][j0]);
+      if (FAST) {
+        float2 tM2 = make_float2(0.f, 0.f), tD2 = make_float2(0.f, 0.f);
+        const float2 ri2 = make_float2(ri, ri), m2s2 = make_float2(m2s, m2s), nc2 = make_float2(negc_last, negc_last);
+        const float2 half2c = make_float2(0.5f, 0.5f), rc2 = make_float2(rc, rc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 rj = cr4[q], aj = ca4[q];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int j = q * 4 + hh * 2;
+            const float2 rj2 = hh ? make_float2(rj.z, rj.w) : make_float2(rj.x, rj.y);
+            const float2 aj2 = hh ? make_float2(aj.z, aj.w) : make_float2(aj.x, aj.y);
+            const float2 s2 = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            const float2 lraw = fma2(m2s2, s2, add2(ri2, rj2));
+            const float2 L = make_float2(fmaxf(lraw.x, 0.f), fmaxf(lraw.y, 0.f));
+            const float2 t = mul2(L, nc2);
+            const float2 e4 = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+            const float2 e3 = mul2(e4, e4);
+            const float2 e2 = mul2(e3, e3);
+            const float2 e1 = mul2(e2, e2);
+            const float2 e0 = mul2(e1, e1);
+            const float2 Q = fma2(fma2(fma2(fma2(e4, half2c, e3), half2c, e2), half2c, e1), half2c, e0);
+            const float2 aQ = mul2(aj2, Q);
+            if (FUSED) {
+              const float2 K = add2(add2(add2(e0, e1), add2(e2, e3)), e4);
+              tM2 = fma2(aj2, K, tM2);
+              tD2 = fma2(aQ, L, tD2);
+            }
+            // the clamp mask [L_raw >= 0] is not applied to G: a pair with L_raw < 0 is a numerical duplicate
+            // (z_i = z_j up to rounding), whose term G_ij (z_i - z_j) vanishes whatever G_ij is
+            float2 gv = mul2(aQ, rc2);
+            if (!FUSED) {
+              gv.x += (aj2.x != 0.f && lraw.x >= 0.f) ? cval : 0.f;
+              gv.y += (aj2.y != 0.f && lraw.y >= 0.f) ? cval : 0.f;
+            }
+            if (H16) {
+              const uint32_t pk = pack_half2(gv.x, gv.y);
+              gp[j >> 1] = pk;
+              rowsum = add_half2_f32(rowsum, pk);
+            } else {
+              const float g0 = to_tf32(gv.x), g1 = to_tf32(gv.y);
+              gp[j] = __float_as_uint(g0);
+              gp[j + 1] = __float_as_uint(g1);
+              rowsum += g0 + g1;
+            }
+          }
+        }
+        if (FUSED) {
+          accM += (double)(ai_m * (tM2.x + tM2.y));
+          accD += (double)(ai_m * (tD2.x + tD2.y));
+        }
+      } else {
+        float tM = 0.f, tD = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float2 ci = ctl->colinfo[b][j0 + j];
-          const float Lraw = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
+          const float rj = ctl->col_r[b][j0 + j], aj = ctl->col_a[b][j0 + j];
+          const float Lraw = fmaf(m2s, __uint_as_float(v[j]), ri + rj);
           const float L = fmaxf(Lraw, 0.f);
           float K, Q;
-          kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+          kernel_terms<false>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
           if (FUSED) {
-            tM = fmaf(ci.y, K, tM);
-            tD = fmaf(ci.y * L, Q, tD);
+            tM = fmaf(aj, K, tM);
+            tD = fmaf(aj * L, Q, tD);
           }
-          float gv = FUSED ? (ci.y * Q) * nai_sig : fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);
-          gv = (Lraw >= 0.f) ? gv : 0.f;
+          float gv = (aj * Q) * rc;
+          if (!FUSED) gv += (aj != 0.f && Lraw >= 0.f) ? cval : 0.f;
           if (H16) {
-            const float gh = __half2float(__float2half_rn(gv * gs));   // the value the tensor core will see
-            gq[j] = gh;
-            rowsum = fmaf(gh, gs_inv, rowsum);
+            const __half hv = __float2half_rn(gv);
+            const uint32_t hb = (uint32_t)__half_as_ushort(hv);
+            if (j & 1) gp[j >> 1] |= hb << 16; else gp[j >> 1] = hb;
+            rowsum += __half2float(hv);
           } else {
-            const float gh = to_tf32(gv);
-            gq[j] = gh;
-            rowsum += gh;
+            const float g0 = to_tf32(gv);
+            gp[j] = __float_as_uint(g0);
+            rowsum += g0;
           }
         }
-        if (H16) {
-          // 32 halfs = 64 bytes = four 16-byte chunks of row r in K-atom (j0 / 64), 128-byte swizzle
-          uint8_t *atom = g_smem + (j0 >> 6) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
-          const int cb = (j0 & 63) >> 3;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const __half2 h0 = __floats2half2_rn(gq[q4 * 8 + 0], gq[q4 * 8 + 1]);
-            const __half2 h1 = __floats2half2_rn(gq[q4 * 8 + 2], gq[q4 * 8 + 3]);
-            const __half2 h2 = __floats2half2_rn(gq[q4 * 8 + 4], gq[q4 * 8 + 5]);
-            const __half2 h3 = __floats2half2_rn(gq[q4 * 8 + 6], gq[q4 * 8 + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<const uint32_t *>(&h0);
-            pk.y = *reinterpret_cast<const uint32_t *>(&h1);
-            pk.z = *reinterpret_cast<const uint32_t *>(&h2);
-            pk.w = *reinterpret_cast<const uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) = pk;
-          }
-        } else {
-          uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4)
-            *reinterpret_cast<float4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
-                make_float4(gq[q4 * 4 + 0], gq[q4 * 4 + 1], gq[q4 * 4 + 2], gq[q4 * 4 + 3]);
+        if (FUSED) {
+          accM += (double)(ai_m * tM);
+          accD += (double)(ai_m * tD);
         }
       }
-      if (FUSED) {
-        accM += (double)(ai_m * tM);
-        accD += (double)(ai_m * tD);
+      // ---- G row segment -> shared memory (K-major, 128-byte swizzle), once P(g - GB) has consumed the buffer ----
+      mbar_wait(&ctl->g_empty[gb], (gu & 1) ^ 1);
+      uint8_t *gbuf = g_smem + gb * Cfg::G_BYTES;
+      if (H16) {
+        // 32 halfs = 64 bytes = four 16-byte chunks of row r in K-atom (j0 / 64)
+        uint8_t *atom = gbuf + (j0 >> 6) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+        const int cb = (j0 & 63) >> 3;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) =
+              make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
+      } else {
+        uint8_t *atom = gbuf + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
+              make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
       }
-      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(g_full_leader);
-        mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->s_empty[b]), 0));
-      }
+      if (lane == 0) mbar_arrive_cluster(g_full_leader0 + 8u * (uint32_t)gb);
     }
     if (FUSED && blockIdx.y == 0) {
 #pragma unroll
@@ -2098,11 +2207,11 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         ctl->red[ew][0] = accM;
         ctl->red[ew][1] = accD;
       }
-      named_barrier_sync(1, BWD_EPI_THREADS);
+      named_barrier_sync(1, SW_EPI_THREADS);
       if (et == 0) {
         double m = 0.0, dd = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < SW_EPI_WARPS; ++k) {
           m += ctl->red[k][0];
           dd += ctl->red[k][1];
         }
@@ -2122,14 +2231,16 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         }
       }
     }
-    // ---- row sums of G: 4 partials per row (2 lane halves x 2 column halves) -> all 128 rows in both CTAs ----
-    named_barrier_sync(1, BWD_EPI_THREADS);
-    float *part = reinterpret_cast<float *>(&ctl->colinfo[0][0]);   // [4][64]
-    float *rs_all = reinterpret_cast<float *>(&ctl->colinfo[1][0]); // [128]
-    part[(jh * 2 + ch) * 64 + r] = rowsum;
-    named_barrier_sync(1, BWD_EPI_THREADS);
+    // ---- row sums of G: 8 partials per row (2 lane halves x 4 column chunks) -> all 128 rows in both CTAs ----
+    named_barrier_sync(1, SW_EPI_THREADS);
+    float *part = &ctl->col_r[0][0];                       // [8][64] (col_r[0..1] are contiguous)
+    float *rs_all = ctl->rs_all;
+    part[(jh * 4 + cq) * 64 + r] = rowsum * gs_inv;
+    named_barrier_sync(1, SW_EPI_THREADS);
     if (et < 64) {
-      const float tot = (part[et] + part[64 + et]) + (part[128 + et] + part[192 + et]);
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot += part[k * 64 + et];
       rs_all[rank * 64 + et] = tot;
       st_cluster_f32(mapa_u32(smem_u32(&rs_all[rank * 64 + et]), rank ^ 1u), tot);
     }
@@ -2141,9 +2252,9 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     // ===================== write-out: dZ[i, f] = coef (rowsum_i z_i[f] - dZ^T[f, i]) =====================
     const int ew = warp - 2;
     const int lg = warp & 3;
-    const int ch = ew >> 2;
+    const int cq = ew >> 2;
     const int tl = lg * 32 + lane;
-    const float *rs_all = reinterpret_cast<const float *>(&ctl->colinfo[1][0]);
+    const float *rs_all = ctl->rs_all;
     float coef = 1.f;
     if (!FUSED) {
       const float M = p.stats[EDRL_MMD_STAT_M];
@@ -2168,14 +2279,12 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       frexpf(qmax / (sigma0 * nmin * nmin), &ex);
       gs_inv = ldexpf(1.f, ex - 14);
     }
-    for (int t = 0; t < ntile; ++t) {
-      const int f = f0 + t * 256 + (int)rank * 128 + tl;
-      const bool f_ok = f < p.d;
-      const float unscale = (H16 && f_ok) ? ldexpf(gs_inv, -p.fscale[f]) : 1.f;     // and of column f of Z^T
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int i0 = ch * 64 + c2 * 32;
-        if (i0 >= rows_here) break;
+    const int i0 = cq * 32;
+    if (i0 < rows_here) {
+      for (int t = 0; t < ntile; ++t) {
+        const int f = f0 + t * 256 + (int)rank * 128 + tl;
+        const bool f_ok = f < p.d;
+        const float unscale = (H16 && f_ok) ? ldexpf(gs_inv, -p.fscale[f]) : 1.f;     // and of column f of Z^T
         uint32_t v[32];
         tmem_ld_32x32(tmem_dz + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BN + i0), v);
         tmem_ld_wait();
@@ -2256,13 +2365,13 @@ static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt
   return 0;
 }
 
-template <bool FAST, bool FUSED, bool H16 = false>
+template <bool FAST, bool FUSED, int MODE = 0>
 static int launch_sweep256_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z128, const CUtensorMap &tm_zt,
                              const BwdParams &p, dim3 grid, cudaStream_t st) {
-  auto kern = mmd_sweep256_kernel<FAST, FUSED, H16>;
-  constexpr int SMEM = SweepCfg<H16>::SMEM_BYTES;
+  auto kern = mmd_sweep256_kernel<FAST, FUSED, MODE>;
+  constexpr int SMEM = SweepCfg<MODE>::SMEM_BYTES;
   EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  kern<<<grid, BWD_THREADS, SMEM, st>>>(tm_z64, tm_z128, tm_zt, p);
+  kern<<<grid, SW_THREADS, SMEM, st>>>(tm_z64, tm_z128, tm_zt, p);
   EDRL_LAUNCHED();
   return 0;
 }
@@ -2426,13 +2535,20 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
   if (L.h16) {
-    // TF32 Gram, binary16 (scaled) operands for G.Z
+    // binary16 (scaled) operands for G.Z; the Gram on TF32 (TF32H) or on the binary16 copy Z16 (F16S)
     CUtensorMap tm_z128, tm_zt16;
-    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
     if (int rc = make_tmap_2d_f16(&tm_zt16, ws + L.off_zt16, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 2, 128, 64)) return rc;
     grid2.z = 1;
-    if (fast) return launch_sweep256_t<true, true, true>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-    return launch_sweep256_t<false, true, true>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    if (L.s16) {
+      CUtensorMap tm_z64h;
+      if (int rc = make_tmap_2d_f16(&tm_z64h, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 64, 64)) return rc;
+      if (int rc = make_tmap_2d_f16(&tm_z128, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 128, 64)) return rc;
+      if (fast) return launch_sweep256_t<true, true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+      return launch_sweep256_t<false, true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+    }
+    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (fast) return launch_sweep256_t<true, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    return launch_sweep256_t<false, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
   }
   if (use_sweep256() && grid2.z == 1) {
     CUtensorMap tm_z128;

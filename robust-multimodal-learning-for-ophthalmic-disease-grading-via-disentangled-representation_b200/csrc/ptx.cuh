@@ -351,6 +351,47 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
 }
 
 // ---------------------------------------------------------------- misc math
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): one issue slot for two elements.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+        "l"(*reinterpret_cast<unsigned long long *>(&c)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+  return *reinterpret_cast<float2 *>(&d);
+}
+// (lo, hi) -> packed binary16 pair, round to nearest even (F2FP.F16.F32.PACK_AB)
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// acc += lo + hi of a packed binary16 pair, each add in fp32 (FHADD: no unpack instruction)
+__device__ __forceinline__ float add_half2_f32(float acc, uint32_t pk) {
+  asm("{\n\t"
+      ".reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %1;\n\t"
+      "add.rn.f32.f16 %0, l, %0;\n\t"
+      "add.rn.f32.f16 %0, h, %0;\n\t"
+      "}\n"
+      : "+f"(acc)
+      : "r"(pk));
+  return acc;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));

@@ -20,7 +20,11 @@ FLAG_3XTF32 = 1
 FLAG_TF32H = 2
 # "tf32h": TF32 Gram like "tf32"; the G.Z product of the fused training sweep reads G and Z as power-of-two-scaled
 # binary16 -- the same 11-bit significands as their TF32 roundings, half the bytes through shared memory.
-_PRECISIONS = {"tf32": FLAG_TF32, "3xtf32": FLAG_3XTF32, "tf32h": FLAG_TF32H}
+FLAG_F16S = 4
+# "f16s": like "tf32h", and the Gram of the fused sweep reads a binary16 copy of the same TF32-rounded operand (one
+# power-of-two scale for the whole matrix): identical significands and exact products, both contractions on kind::f16.
+_PRECISIONS = {"tf32": FLAG_TF32, "3xtf32": FLAG_3XTF32, "tf32h": FLAG_TF32H, "f16s": FLAG_F16S}
+_FUSED_FLAGS = (FLAG_TF32, FLAG_TF32H, FLAG_F16S)
 _default_precision = os.environ.get("EDRL_MMD_PRECISION", "tf32").lower()
 NUM_STATS = 8
 # TF32 training steps use the fused pass (forward sums + gradient in one sweep over the Gram tiles);
@@ -85,7 +89,7 @@ class _MKMMDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x.device)
         ctx.U = None
-        if _FUSED and flags in (FLAG_TF32, FLAG_TF32H) and any(ctx.needs_input_grad[:2]):
+        if _FUSED and flags in _FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
             # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
             slabs = int(lib.edrl_mmd_grad_slabs(n_s, n_t, n_s + n_t))
             u = torch.empty(slabs, n_s + n_t, d, dtype=torch.float32, device=x.device)

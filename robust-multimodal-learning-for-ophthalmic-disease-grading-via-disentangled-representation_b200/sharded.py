@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 from . import _lib
 from . import mmd as _mmd
-from .mmd import FLAG_TF32, FLAG_TF32H, NUM_STATS, Workspace, _flags
+from .mmd import FLAG_TF32, NUM_STATS, Workspace, _flags
 
 TILE = 128   # Gram tile edge of csrc/mmd.cu (BM = BN)
 
@@ -95,7 +95,7 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=x_all.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x_all.device)
         ctx.U = None
-        if _mmd._FUSED and flags in (FLAG_TF32, FLAG_TF32H) and any(ctx.needs_input_grad[:2]):
+        if _mmd._FUSED and flags in _mmd._FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
             # fused pass over this rank's rows (source rows, then target rows): partial sums + gradient part U
             (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
             slabs = int(lib.edrl_mmd_grad_slabs(plan.n_s, plan.n_t, c0 + c1))

@@ -5,6 +5,7 @@ Tolerances (written here as the contract):
   3xTF32 mode : loss rtol 1e-4 (+ atol 1e-6), gradients 1e-4 * |grad|_inf absolute
   TF32 mode   : loss rtol 1e-3 (+ atol 1e-6), gradients 2e-3 * |grad|_inf absolute
   TF32H mode  : the same bar as TF32 (TF32 Gram; G.Z operands as scaled binary16 with the same 11-bit significands)
+  F16S mode   : the same bar as TF32 (the Gram too reads a scaled binary16 copy of the TF32-rounded operand)
 against the fp64 reference/oracle value.
 """
 import os
@@ -19,7 +20,7 @@ from oracle.gen_golden import MMD_CASES, MMD_VARIANTS, mmd_inputs
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_gpu(), reason="needs a CUDA device")]
 
-MODES = [("3xtf32", 1, 1e-4, 1e-4), ("tf32", 0, 1e-3, 2e-3), ("tf32h", 2, 1e-3, 2e-3)]   # name, flag, loss rtol, grad atol / |g|_inf
+MODES = [("3xtf32", 1, 1e-4, 1e-4), ("tf32", 0, 1e-3, 2e-3), ("tf32h", 2, 1e-3, 2e-3), ("f16s", 4, 1e-3, 2e-3)]   # name, flag, loss rtol, grad atol / |g|_inf
 
 
 @pytest.fixture(scope="module")
@@ -398,13 +399,14 @@ def test_ragged_shapes_vs_oracle(ns, nt, d, mode):
     assert np.isclose(l0.item(), ref, rtol=ltol, atol=1e-6)
 
 
-def test_tf32h_is_numerically_the_tf32_result():
-    """The binary16 copies carry the same 11-bit significands as the TF32 operands, so the two modes agree far
-    inside the TF32 tolerance (only round-half tie-breaking of G and binary16 underflow can differ)."""
+def test_binary16_container_modes_are_numerically_the_tf32_result():
+    """The binary16 copies carry the same 11-bit significands as the TF32 operands, so the modes agree far
+    inside the TF32 tolerance (only round-half tie-breaking of G, the accumulation order inside the tensor core and
+    binary16 underflow can differ)."""
     import edrl_b200
     x, y = mmd_inputs(1011, 1024, 768, 512, 0.1, 1.25)
     outs = {}
-    for prec in ("tf32", "tf32h"):
+    for prec in ("tf32", "tf32h", "f16s"):
         xt = dev(x.numpy()).requires_grad_(True)
         yt = dev(y.numpy()).requires_grad_(True)
         l = edrl_b200.MK_MMD(xt, yt, precision=prec)
@@ -414,12 +416,18 @@ def test_tf32h_is_numerically_the_tf32_result():
     gmax = outs["tf32"][1].abs().max().item()
     assert (outs["tf32"][1] - outs["tf32h"][1]).abs().max().item() <= 2e-5 * gmax
     assert (outs["tf32"][2] - outs["tf32h"][2]).abs().max().item() <= 2e-5 * gmax
-    # badly scaled columns (1e-6 .. 1e6) exercise the per-column binary16 scale
+    # F16S: the Gram operands are the same values too; only the fp32 accumulation order inside the MMA differs
+    assert abs(outs["tf32"][0] - outs["f16s"][0]) <= 2e-6 * abs(outs["tf32"][0])
+    assert (outs["tf32"][1] - outs["f16s"][1]).abs().max().item() <= 5e-5 * gmax
+    assert (outs["tf32"][2] - outs["f16s"][2]).abs().max().item() <= 5e-5 * gmax
+    # badly scaled columns (1e-6 .. 1e6) exercise the per-column binary16 scale (and, for F16S, binary16 underflow
+    # of the small columns in the Gram operand -- they do not contribute to an fp32 distance anyway)
     scale = torch.logspace(-6, 6, 512, dtype=torch.float64)
     xs, ys = (x * scale).numpy(), (y * scale).numpy()
-    xt = dev(xs).requires_grad_(True)
-    l = edrl_b200.MK_MMD(xt, dev(ys), precision="tf32h")
-    l.backward()
     ref, _, dxr, _ = O.mk_mmd_grad(xs, ys)
-    assert np.isclose(l.item(), ref, rtol=1e-3)
-    assert np.abs(xt.grad.cpu().numpy() - dxr).max() <= 2e-3 * np.abs(dxr).max()
+    for prec in ("tf32h", "f16s"):
+        xt = dev(xs).requires_grad_(True)
+        l = edrl_b200.MK_MMD(xt, dev(ys), precision=prec)
+        l.backward()
+        assert np.isclose(l.item(), ref, rtol=1e-3), prec
+        assert np.abs(xt.grad.cpu().numpy() - dxr).max() <= 2e-3 * np.abs(dxr).max(), prec
