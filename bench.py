@@ -588,7 +588,7 @@ def run_ours(args, rank, local_rank, world):
         loss_t = torch.empty((), device=dev)
         stats = torch.empty(8, device=dev)
         gout = torch.ones((), device=dev)
-        dz = torch.empty(int(lib.edrl_mmd_grad_slabs(N, N, n)) * n, d, device=dev)
+        dz = torch.empty(int(lib.edrl_mmd_grad_slabs(N, N, d, flags, n, 0)) * n, d, device=dev)
         st = _lib.stream_and_device(xa)
 
         def fwd_only():

@@ -100,10 +100,12 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                       int row_begin, int row_count, float *dZ,
                       void *workspace, size_t workspace_bytes, void *stream);
 
-/* Fused training pass (TF32 only): forward block sums AND the bandwidth-independent part of the gradient in one
+/* Fused training pass (TF32 / TF32H / F16S): forward block sums AND the bandwidth-independent part of the gradient in one
  * sweep over the Gram tiles of rows [row_begin, row_begin + row_count) -- a training step then visits every tile
  * once instead of 1.5 times (edrl_mmd_forward + edrl_mmd_backward).  Same math as code/MMD.py:16-72 + autograd:
- *   U[i, :] = rowsum(G')_i z_i - (G' Z)_i,  G'_ij = -a_i a_j Q_ij / sigma_0 [L_raw >= 0]
+ *   U[i, :] = rowsum(G')_i z_i - (G' Z)_i,  G'_ij = -a_i a_j Q_ij / sigma_0
+ *     (the clamp mask [L_raw >= 0] of code/MMD.py:27 is not applied to G': a pair with L_raw < 0 is a numerical
+ *      duplicate, z_i = z_j up to rounding, and its term G'_ij (z_i - z_j) vanishes whatever G'_ij is)
  *                                          -> U [edrl_mmd_grad_slabs(...), rows, d], partial sums over column slabs
  *   partial sums (sum a_i a_j K_ij, sum a_i a_j L_ij Q_ij over the rows of this call) are ADDED into the
  *   workspace accumulators; finalize != 0 (the call covers all rows): loss / stats are written as by
@@ -112,9 +114,10 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
  * in closed form (sum_j c (z_i - z_j) = c n z_i for centred Z).  dZ may alias U.  An optional second row range
  * (row_count2 > 0, after the first) lets a rank of a sharded evaluation cover its source rows and its target rows
  * in one launch; U / dZ hold range 1's rows followed by range 2's. */
-/* Number of partial output slabs the fused pass writes for `rows` output rows (it splits its column sweep to
- * balance the last wave of row panels over the SM pairs): U must hold slabs * rows * d floats; apply_grad sums them. */
-int edrl_mmd_grad_slabs(int n_s, int n_t, int rows);
+/* Number of partial output slabs the fused pass may write for row_count + row_count2 output rows: the row panels that
+ * do not fill a whole wave of SM pairs have their column sweep split into that many slabs (one partial output each).
+ * U must hold slabs * (row_count + row_count2) * d floats; apply_grad sums the slabs a row was split into. */
+int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2);
 int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                           int flags, int row_begin, int row_count, int row_begin2, int row_count2, int finalize,
                           float *loss, float *stats, double *partial, float *U, void *workspace,

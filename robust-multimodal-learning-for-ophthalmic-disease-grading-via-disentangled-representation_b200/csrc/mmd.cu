@@ -855,6 +855,9 @@ struct BwdParams {
   int n_t, finalize;
   int row_begin2, row_count2;      // optional second row range (a rank's target rows); output rows follow range 1
   const int *fscale;               // TF32H: binary16 scale exponent per feature column
+  // mmd_sweep256_kernel work list (make_plan): virtual panel = (feature pass, row panel); the first `full_items` virtual
+  // panels sweep all column groups, every later one is split into `split` column slabs with one partial output each
+  int panels, full_items, split, ticket_total;
 };
 
 // ring order (producer and MMA issuer walk the same sequence):
@@ -1835,7 +1838,21 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
-  const int panel = blockIdx.x >> 1;
+  // work item -> (virtual panel, column slab): see make_plan
+  const int item = blockIdx.x >> 1;
+  const int nG_all = p.nb / 2;                            // groups of 256 columns (n_pad is a multiple of 256)
+  int vp, g_begin, g_end, slab;
+  if (item < p.full_items) {
+    vp = item; slab = 0; g_begin = 0; g_end = nG_all;
+  } else {
+    const int q = item - p.full_items;
+    vp = p.full_items + q / p.split;
+    slab = q % p.split;
+    g_begin = (int)((long long)slab * nG_all / p.split);
+    g_end = (int)((long long)(slab + 1) * nG_all / p.split);
+  }
+  const int ypass = vp / p.panels;
+  const int panel = vp - ypass * p.panels;
   const int np1 = (p.row_count + BM - 1) / BM;
   const bool second = panel >= np1;
   const int lpanel = second ? panel - np1 : panel;
@@ -1843,8 +1860,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int rng_count = second ? p.row_count2 : p.row_count;
   const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;
   const int row_base = rng_begin + lpanel * BM;
-  const int f0 = blockIdx.y * P2_FEATS;
-  const int nG = p.nb / 2;                                // groups of 256 columns (n_pad is a multiple of 256)
+  const int f0 = ypass * P2_FEATS;
+  const int nG = g_end - g_begin;                         // this item's column groups: g_begin + [0, nG)
   const int kchunks = S16 ? p.d_pad / 64 : p.kchunks;     // 128-byte K chunks of an S operand row; even
   const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;
 
@@ -1899,7 +1916,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     };
     const int irow = row_base + (int)rank * 64;
     auto load_S = [&](int g) {
-      const int jrow = g * Q_GROUP + (int)rank * 128;
+      const int jrow = (g_begin + g) * Q_GROUP + (int)rank * 128;
       for (int kc = 0; kc < kchunks; kc += 2) {
         {                                                   // two chunks of this CTA's 64 panel rows
           uint8_t *st = acquire();
@@ -1922,7 +1939,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
           uint8_t *st = acquire();
           const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_zt, bar, g * Q_GROUP + a8 * Cfg::P_ATOM_COLS, f0 + t * 256 + (int)rank * 128);
+          tma_load_2d_pair_elect(st, &tm_zt, bar, (g_begin + g) * Q_GROUP + a8 * Cfg::P_ATOM_COLS,
+                                 f0 + t * 256 + (int)rank * 128);
           next();
         }
     };
@@ -2053,7 +2071,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       gs_inv = ldexpf(1.f, ex - 14);
     }
     const float rc = (-ai / sigma0) * gs;                   // G'_ij 2^eg = (a_j Q_ij) rc
-    const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
+    const bool count_row = FUSED && ypass == 0 && (gi - rng_begin) < rng_count && gi < p.n;
     const float ai_m = count_row ? ai : 0.f;
     double accM = 0.0, accD = 0.0;
     // S16: the tensor core saw Z 2^e on both sides: S = 2^(2e) z_i . z_j
@@ -2063,8 +2081,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     // (r_j, a_j) of the next group: fetched one group ahead by the first 256 epilogue threads
     float nxt_r = 0.f, nxt_a = 0.f;
     if (et < Q_GROUP) {
-      nxt_r = (float)p.racc[et];
-      nxt_a = p.a[et];
+      nxt_r = (float)p.racc[g_begin * Q_GROUP + et];
+      nxt_a = p.a[g_begin * Q_GROUP + et];
     }
 
     for (int g = 0; g < nG; ++g) {
@@ -2076,8 +2094,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         ctl->col_r[b][et] = nxt_r;
         ctl->col_a[b][et] = nxt_a;
         if (g + 1 < nG) {
-          nxt_r = (float)p.racc[(g + 1) * Q_GROUP + et];
-          nxt_a = p.a[(g + 1) * Q_GROUP + et];
+          nxt_r = (float)p.racc[(g_begin + g + 1) * Q_GROUP + et];
+          nxt_a = p.a[(g_begin + g + 1) * Q_GROUP + et];
         }
       }
       named_barrier_sync(1, SW_EPI_THREADS);
@@ -2197,7 +2215,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(g_full_leader0 + 8u * (uint32_t)gb);
     }
-    if (FUSED && blockIdx.y == 0) {
+    if (FUSED && ypass == 0) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         accM += __shfl_xor_sync(0xffffffffu, accM, o);
@@ -2219,7 +2237,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         atomicAdd(p.acc + 1, dd);
         __threadfence();
         const unsigned t = atomicAdd(p.ticket, 1u);
-        if (t == gridDim.x - 1) {
+        if (t == (unsigned)p.ticket_total - 1u) {
           __threadfence();
           const double Mv = atomicAdd(p.acc + 0, 0.0);
           const double Ds = atomicAdd(p.acc + 1, 0.0);
@@ -2290,7 +2308,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         tmem_ld_wait();
         if (f_ok) {
           const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
-          float *oc = p.dz + (size_t)(out_row0 + i0) * p.d + f;
+          float *oc = p.dz + ((size_t)slab * (p.row_count + p.row_count2) + out_row0 + i0) * p.d + f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (i0 + j < rows_here)
@@ -2317,7 +2335,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(128)
 mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const double *__restrict__ colsum_hi,
                       const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
-                      int row_begin2, int row_count2, int d, int d_pad, int n, int nslab, float *__restrict__ dz) {
+                      int row_begin2, int row_count2, int d, int d_pad, int n, int panels, int full_items, int split,
+                      float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
@@ -2329,8 +2348,11 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
   const float *zr = zhi + gr * d_pad;
   const float *ur = U + (size_t)r * d;
   float *orow = dz + (size_t)r * d;
+  // the sweep's work list (make_plan): virtual panel (feature pass, row panel) >= full_items was swept in `split` slabs
+  const int panel = (r < row_count) ? r / BM : (row_count + BM - 1) / BM + (r - row_count) / BM;
   if (VEC4) {
     for (int f = (blockIdx.y * 128 + threadIdx.x) * 4; f < d; f += gridDim.y * 512) {
+      const int nslab = ((f / P2_FEATS) * panels + panel < full_items) ? 1 : split;
       float4 u = *reinterpret_cast<const float4 *>(ur + f);
       for (int sl = 1; sl < nslab; ++sl) {
         const float4 w = *reinterpret_cast<const float4 *>(ur + sl * slab + f);
@@ -2346,6 +2368,7 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
     }
   } else {
     for (int f = blockIdx.y * 128 + threadIdx.x; f < d; f += gridDim.y * 128) {
+      const int nslab = ((f / P2_FEATS) * panels + panel < full_items) ? 1 : split;
       float u = ur[f];
       for (int sl = 1; sl < nslab; ++sl) u += ur[sl * slab + f];
       dz[(size_t)r * d + f] = coef * fmaf(cv, fmaf(fn, __ldg(zr + f), -(float)colsum_hi[f]), u);
@@ -2376,12 +2399,51 @@ static int launch_sweep256_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z1
   return 0;
 }
 
-static bool use_sweep256() {
-  // 256-column S tiles are the default for the fused sweep (1.16 -> 1.02 ms at N=8192, d=512);
-  // EDRL_MMD_SWEEP256=0 selects mmd_bwd_pair_kernel<.., FUSED> (128-column tiles, half-resident Z_I) for A/B runs
-  static const char *env = getenv("EDRL_MMD_SWEEP256");
-  return env == nullptr || atoi(env) != 0;
+// Work list of the fused sweep.  A virtual panel is (feature pass of 512 columns, 128-row panel); one CTA pair sweeps it.
+// P virtual panels on C = SMs / 2 pairs run in ceil(P / C) waves, e.g. 128 panels on 74 pairs take 2 waves for 1.73 waves
+// of work.  The first floor(P / C) C panels are swept whole; each of the rest is split into `split` column slabs (one
+// partial output per slab, summed by edrl_mmd_apply_grad) so that the last wave is (nearly) full: 128 -> 74 whole panels
+// + 54 x 4 quarter sweeps = 1.75 waves.  Small problems (P < C) are split the same way to fill the machine.
+struct SweepPlan {
+  int panels;       // row panels
+  int vpanels;      // panels x feature passes
+  int full_items;   // virtual panels swept whole
+  int split;        // column slabs of every later virtual panel (1, 2, 4 or 8)
+  int items;        // CTA pairs to launch
+  int items_pass0;  // of which belong to feature pass 0 (they carry the forward sums)
+};
+
+static SweepPlan make_plan(const Layout &L, int row_count, int row_count2) {
+  SweepPlan pl;
+  pl.panels = (row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM;
+  const int ny = (L.d_pad + P2_FEATS - 1) / P2_FEATS;
+  pl.vpanels = pl.panels * ny;
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int C = sms / 2 > 0 ? sms / 2 : 1;
+  const int nG = L.n_pad / Q_GROUP;
+  pl.full_items = (pl.vpanels / C) * C;
+  const int R = pl.vpanels - pl.full_items;
+  pl.split = 1;
+  static const char *env = getenv("EDRL_MMD_SLABS");      // =1: never split (A/B runs)
+  const int kmax = env ? atoi(env) : 8;
+  if (R > 0) {
+    double best = 1.0;
+    for (int k = 2; k <= 8 && k <= kmax && k <= nG; k *= 2) {
+      const double t = (double)((R * k + C - 1) / C) / k;
+      if (t < best - 1e-9) {
+        best = t;
+        pl.split = k;
+      }
+    }
+  }
+  if (pl.split == 1) pl.full_items = pl.vpanels;
+  pl.items = pl.full_items + (pl.vpanels - pl.full_items) * pl.split;
+  const int full0 = pl.full_items < pl.panels ? pl.full_items : pl.panels;
+  pl.items_pass0 = full0 + (pl.panels - full0) * pl.split;
+  return pl;
 }
+
 
 }  // namespace mmd
 }  // namespace edrl
@@ -2482,19 +2544,9 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   return launch_bwd_t<false, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
 }
 
-int edrl_mmd_grad_slabs(int n_s, int n_t, int rows) {
-  // The fused pass can split its column sweep into slabs (gridDim.z) with one partial output each.  Measured at
-  // N=8192, d=512 (128 panels on 74 SM pairs): 1 slab 1.165 ms, 2 -> 1.21, 4 -> 1.18, 8 -> 1.37: the sweep is bound by
-  // the chip-wide L2 -> SM rate, so a short last wave already runs faster per cluster and splitting only adds
-  // set-up and output traffic.  Default 1; EDRL_MMD_SLABS overrides for experiments.
-  if (n_s <= 0 || n_t <= 0 || rows <= 0) return 1;
-  static const char *env = getenv("EDRL_MMD_SLABS");
-  if (env) {
-    const int v = atoi(env);
-    const int nJ = (int)align_up((size_t)n_s + n_t, 256) / BN;
-    if (v > 1 && nJ / v >= 1) return v;
-  }
-  return 1;
+int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2) {
+  if (n_s <= 0 || n_t <= 0 || d <= 0 || row_count <= 0 || row_count2 < 0) return 1;
+  return make_plan(make_layout(n_s, n_t, d, flags), row_count, row_count2).split;
 }
 
 int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
@@ -2530,15 +2582,15 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
   p.partial = partial; p.loss = loss; p.stats_out = stats;
   p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
-  dim3 grid2(2 * ((row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS,
-             edrl_mmd_grad_slabs(n_s, n_t, row_count + row_count2));
+  const SweepPlan pl = make_plan(L, row_count, row_count2);
+  p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.ticket_total = 2 * pl.items_pass0;
+  dim3 grid2(2 * pl.items, 1, 1);
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
   if (L.h16) {
     // binary16 (scaled) operands for G.Z; the Gram on TF32 (TF32H) or on the binary16 copy Z16 (F16S)
     CUtensorMap tm_z128, tm_zt16;
     if (int rc = make_tmap_2d_f16(&tm_zt16, ws + L.off_zt16, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 2, 128, 64)) return rc;
-    grid2.z = 1;
     if (L.s16) {
       CUtensorMap tm_z64h;
       if (int rc = make_tmap_2d_f16(&tm_z64h, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 64, 64)) return rc;
@@ -2550,18 +2602,12 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
     if (fast) return launch_sweep256_t<true, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
     return launch_sweep256_t<false, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
   }
-  if (use_sweep256() && grid2.z == 1) {
+  {
     CUtensorMap tm_z128;
     if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
     if (fast) return launch_sweep256_t<true, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
     return launch_sweep256_t<false, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
   }
-  if (L.d_pad <= 512) {
-    if (fast) return launch_bwd_pair_t<true, 8, true>(tm_z64, tm_zt, p, grid2, st);
-    return launch_bwd_pair_t<false, 8, true>(tm_z64, tm_zt, p, grid2, st);
-  }
-  if (fast) return launch_bwd_pair_t<true, 0, true>(tm_z64, tm_zt, p, grid2, st);
-  return launch_bwd_pair_t<false, 0, true>(tm_z64, tm_zt, p, grid2, st);
 }
 
 int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, const float *grad_out,
@@ -2573,7 +2619,7 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n, "MK_MMD apply_grad: bad row range");
   const uint8_t *ws = reinterpret_cast<const uint8_t *>(workspace);
   const int rows = row_count + row_count2;
-  const int nslab = edrl_mmd_grad_slabs(n_s, n_t, rows);
+  const SweepPlan pl = make_plan(L, row_count, row_count2);
   const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
   const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -2581,10 +2627,10 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
   if (v4)
     mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                      row_count2, d, L.d_pad, L.n, nslab, dZ);
+                                                      row_count2, d, L.d_pad, L.n, pl.panels, pl.full_items, pl.split, dZ);
   else
     mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                       row_count2, d, L.d_pad, L.n, nslab, dZ);
+                                                       row_count2, d, L.d_pad, L.n, pl.panels, pl.full_items, pl.split, dZ);
   EDRL_LAUNCHED();
   return 0;
 }

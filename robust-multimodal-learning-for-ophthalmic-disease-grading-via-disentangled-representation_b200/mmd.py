@@ -91,7 +91,7 @@ class _MKMMDFunction(torch.autograd.Function):
         ctx.U = None
         if _FUSED and flags in _FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
             # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
-            slabs = int(lib.edrl_mmd_grad_slabs(n_s, n_t, n_s + n_t))
+            slabs = int(lib.edrl_mmd_grad_slabs(n_s, n_t, d, flags, n_s + n_t, 0))
             u = torch.empty(slabs, n_s + n_t, d, dtype=torch.float32, device=x.device)
             _lib.check(lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul),
                                                  int(kernel_num), flags, 0, n_s + n_t, 0, 0, 1, loss.data_ptr(),

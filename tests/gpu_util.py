@@ -83,7 +83,7 @@ def raw_forward_grad(raw, x, y, r0, c0, r1=0, c1=0, finalize=1, mul=2.0, num=5, 
     loss = torch.zeros((), device="cuda")
     stats = torch.zeros(8, device="cuda")
     partial = torch.zeros(2, dtype=torch.float64, device="cuda")
-    slabs = int(raw.lib.edrl_mmd_grad_slabs(x.shape[0], y.shape[0], c0 + c1))
+    slabs = int(raw.lib.edrl_mmd_grad_slabs(x.shape[0], y.shape[0], x.shape[1], 0, c0, c1))
     u = torch.empty(slabs, c0 + c1, x.shape[1], device="cuda")
     st = raw.L.stream_and_device(x)
     raw.L.check(raw.lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), x.shape[0], y.shape[0], x.shape[1], mul, num,
