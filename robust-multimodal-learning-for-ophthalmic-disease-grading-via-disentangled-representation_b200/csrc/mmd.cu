@@ -43,7 +43,7 @@ struct Layout {
   int n, n_pad, d_pad;
   bool split3, h16, s16;
   size_t off_acc, off_colsum, off_colsum_hi, off_colmax, off_r, off_a, off_fscale, off_zhi, off_zthi, off_zlo, off_ztlo,
-      off_zt16, off_z16, total;
+      off_zt16, off_z16, off_rowsum, total;
   size_t zero_bytes;  // [off_acc, off_acc + zero_bytes) must be cleared before prep
 };
 
@@ -73,6 +73,8 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.off_ztlo = o;     if (L.split3) o += zbytes;
   L.off_zt16 = o;     if (L.h16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z^T [d_pad, n_pad]
   L.off_z16 = o;      if (L.s16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z [n_pad, d_pad]
+  // fused sweep: row sums of G' per (512-column feature pass, column slab), float[passes][8][n_pad]
+  L.off_rowsum = o;   if (!L.split3) o += align_up((size_t)((L.d_pad + 511) / 512) * 8 * L.n_pad * 4, 1024);
   L.total = o;
   return L;
 }
@@ -857,7 +859,8 @@ struct BwdParams {
   const int *fscale;               // TF32H: binary16 scale exponent per feature column
   // mmd_sweep256_kernel work list (make_plan): virtual panel = (feature pass, row panel); the first `full_items` virtual
   // panels sweep all column groups, every later one is split into `split` column slabs with one partial output each
-  int panels, full_items, split, ticket_total;
+  int panels, full_items, split, items;
+  float *rowsum;                   // [feature pass][SW_MAX_SPLIT][n_pad]: rowsum(G')_i per column slab, for apply_grad
 };
 
 // ring order (producer and MMA issuer walk the same sequence):
@@ -1779,10 +1782,11 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 // ring has 9 stages of 16 KiB, G is 64 rows x 256 columns (64 KiB) per CTA.
 constexpr int Q_GROUP = 256;                   // columns per S group
 constexpr int Q_G_BYTES = 8 * P2_CHUNK;        // 64 rows x 256 columns j
-constexpr int Q_CTRL_BYTES = 6144;
+constexpr int Q_CTRL_BYTES = 8192;
 constexpr int SW_EPI_WARPS = 16;               // 4 per TMEM lane group: one 32-column chunk of the S stage each
 constexpr int SW_EPI_THREADS = SW_EPI_WARPS * 32;
 constexpr int SW_THREADS = 64 + SW_EPI_THREADS;
+constexpr int SW_MAX_SPLIT = 8;                // column slabs of a split virtual panel (make_plan)
 
 // MODE 0: TF32 everywhere.  1 (EDRL_MMD_TF32H): binary16 P phase.  2 (EDRL_MMD_F16S): the S phase too reads scaled
 // binary16 operands (Z16, kind::f16): a ring stage then holds 64 feature columns instead of 32.
@@ -1807,20 +1811,61 @@ struct SweepCtrl {
   uint64_t s_empty[2];            // leader, one arrival per epilogue warp of the pair
   uint64_t g_full[2];             // leader, one arrival per epilogue warp of the pair
   uint64_t g_empty[2];            // per CTA (multicast commit)
-  uint64_t dz_full;               // per CTA (multicast commit)
+  uint64_t dz_full;               // per CTA (multicast commit): the item's dZ^T accumulators are complete
+  uint64_t dz_empty;              // leader, one arrival per epilogue warp of the pair: ... and have been read out
   uint32_t tmem_base;
   uint32_t pad;
-  float col_r[2][Q_GROUP];        // r_j per S stage; re-used for the row-sum exchange after the sweep
-  float col_a[2][Q_GROUP];        // a_j per S stage
+  alignas(16) float col_r[2][Q_GROUP];   // r_j per S stage (read as float4)
+  alignas(16) float col_a[2][Q_GROUP];   // a_j per S stage
   float negc[MAX_KERNELS];
   float w[MAX_KERNELS];
   double red[SW_EPI_WARPS][2];
-  float rs_all[BM];               // row sums of G for the panel's 128 rows (both CTAs hold all of them)
+  float part[8][64];              // row-sum partials of an item (2 lane halves x 4 column chunks per row)
 };
 static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
 static_assert(SweepCfg<0>::SMEM_BYTES <= 232448 && SweepCfg<1>::SMEM_BYTES <= 232448, "smem budget");
 
-template <bool FAST, bool FUSED, int MODE>
+// One work item of the sweep (make_plan): a 128-row panel x 512 feature columns, over the column groups
+// [g_begin, g_end) of 256 columns each; split panels write one partial output per slab.
+struct SweepItem {
+  int ypass, slab, g_begin, ng, row_base, out_row0, rng_begin, rng_count, rows_here, f0, ntile;
+};
+__device__ __forceinline__ SweepItem sweep_item(const BwdParams &p, int item) {
+  SweepItem it;
+  const int nG_all = p.nb / 2;                            // n_pad is a multiple of 256
+  int vp, g_end;
+  if (item < p.full_items) {
+    vp = item; it.slab = 0; it.g_begin = 0; g_end = nG_all;
+  } else {
+    const int q = item - p.full_items;
+    vp = p.full_items + q / p.split;
+    it.slab = q % p.split;
+    it.g_begin = (int)((long long)it.slab * nG_all / p.split);
+    g_end = (int)((long long)(it.slab + 1) * nG_all / p.split);
+  }
+  it.ng = g_end - it.g_begin;
+  it.ypass = vp / p.panels;
+  const int panel = vp - it.ypass * p.panels;
+  const int np1 = (p.row_count + BM - 1) / BM;
+  const bool second = panel >= np1;
+  const int lpanel = second ? panel - np1 : panel;
+  it.rng_begin = second ? p.row_begin2 : p.row_begin;
+  it.rng_count = second ? p.row_count2 : p.row_count;
+  it.out_row0 = (second ? p.row_count : 0) + lpanel * BM;
+  it.row_base = it.rng_begin + lpanel * BM;
+  it.f0 = it.ypass * P2_FEATS;
+  it.ntile = (p.d_pad - it.f0 > 256) ? 2 : 1;
+  int rows_here = it.rng_count - lpanel * BM;
+  if (rows_here > BM) rows_here = BM;
+  if (p.n - it.row_base < rows_here) rows_here = p.n - it.row_base;
+  it.rows_here = rows_here;
+  return it;
+}
+
+// Persistent: CTA pair c walks the work items c, c + pairs, c + 2 pairs, ... ; the three roles (TMA producer, MMA
+// issuer, epilogue) each loop over the same item sequence, so the loads and the S phase of the next item run while the
+// epilogue warps still write the previous item out.
+template <bool FAST, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_THREADS, 1)
 mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_z128,
                     const __grid_constant__ CUtensorMap tm_zt, const BwdParams p) {
@@ -1838,32 +1883,9 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
-  // work item -> (virtual panel, column slab): see make_plan
-  const int item = blockIdx.x >> 1;
-  const int nG_all = p.nb / 2;                            // groups of 256 columns (n_pad is a multiple of 256)
-  int vp, g_begin, g_end, slab;
-  if (item < p.full_items) {
-    vp = item; slab = 0; g_begin = 0; g_end = nG_all;
-  } else {
-    const int q = item - p.full_items;
-    vp = p.full_items + q / p.split;
-    slab = q % p.split;
-    g_begin = (int)((long long)slab * nG_all / p.split);
-    g_end = (int)((long long)(slab + 1) * nG_all / p.split);
-  }
-  const int ypass = vp / p.panels;
-  const int panel = vp - ypass * p.panels;
-  const int np1 = (p.row_count + BM - 1) / BM;
-  const bool second = panel >= np1;
-  const int lpanel = second ? panel - np1 : panel;
-  const int rng_begin = second ? p.row_begin2 : p.row_begin;
-  const int rng_count = second ? p.row_count2 : p.row_count;
-  const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;
-  const int row_base = rng_begin + lpanel * BM;
-  const int f0 = ypass * P2_FEATS;
-  const int nG = g_end - g_begin;                         // this item's column groups: g_begin + [0, nG)
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
   const int kchunks = S16 ? p.d_pad / 64 : p.kchunks;     // 128-byte K chunks of an S operand row; even
-  const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (threadIdx.x == 0) {
@@ -1878,6 +1900,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       mbar_init(&ctl->g_empty[s], 1);
     }
     mbar_init(&ctl->dz_full, 1);
+    mbar_init(&ctl->dz_empty, 2 * SW_EPI_WARPS);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -1914,40 +1937,43 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         ph ^= 1;
       }
     };
-    const int irow = row_base + (int)rank * 64;
-    auto load_S = [&](int g) {
-      const int jrow = (g_begin + g) * Q_GROUP + (int)rank * 128;
-      for (int kc = 0; kc < kchunks; kc += 2) {
-        {                                                   // two chunks of this CTA's 64 panel rows
-          uint8_t *st = acquire();
-          const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * Cfg::S_COLS, irow);
-          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * Cfg::S_COLS, irow);
-          next();
-        }
+    for (int item = pair; item < p.items; item += npairs) {
+      const SweepItem it = sweep_item(p, item);
+      const int irow = it.row_base + (int)rank * 64;
+      auto load_S = [&](int g) {
+        const int jrow = (it.g_begin + g) * Q_GROUP + (int)rank * 128;
+        for (int kc = 0; kc < kchunks; kc += 2) {
+          {                                                   // two chunks of this CTA's 64 panel rows
+            uint8_t *st = acquire();
+            const uint32_t bar = full0 + 8u * (uint32_t)s;
+            tma_load_2d_pair_elect(st, &tm_z64, bar, kc * Cfg::S_COLS, irow);
+            tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * Cfg::S_COLS, irow);
+            next();
+          }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
-          uint8_t *st = acquire();
-          const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * Cfg::S_COLS, jrow);
-          next();
+          for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
+            uint8_t *st = acquire();
+            const uint32_t bar = full0 + 8u * (uint32_t)s;
+            tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * Cfg::S_COLS, jrow);
+            next();
+          }
         }
+      };
+      auto load_P = [&](int g) {
+        for (int t = 0; t < it.ntile; ++t)
+          for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
+            uint8_t *st = acquire();
+            const uint32_t bar = full0 + 8u * (uint32_t)s;
+            tma_load_2d_pair_elect(st, &tm_zt, bar, (it.g_begin + g) * Q_GROUP + a8 * Cfg::P_ATOM_COLS,
+                                   it.f0 + t * 256 + (int)rank * 128);
+            next();
+          }
+      };
+      load_S(0);
+      for (int g = 0; g < it.ng; ++g) {
+        if (g + 1 < it.ng) load_S(g + 1);
+        load_P(g);
       }
-    };
-    auto load_P = [&](int g) {
-      for (int t = 0; t < ntile; ++t)
-        for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
-          uint8_t *st = acquire();
-          const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_zt, bar, (g_begin + g) * Q_GROUP + a8 * Cfg::P_ATOM_COLS,
-                                 f0 + t * 256 + (int)rank * 128);
-          next();
-        }
-    };
-    load_S(0);
-    for (int g = 0; g < nG; ++g) {
-      if (g + 1 < nG) load_S(g + 1);
-      load_P(g);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA, warp-converged issue) =====================
@@ -1964,71 +1990,81 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       };
       const uint32_t ring_addr = smem_u32(ring);
       const uint32_t g_addr = smem_u32(g_smem);
-      auto issue_S = [&](int g) {
-        const int b = g & 1;
-        const uint32_t u = (uint32_t)(g >> 1);
-        mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_s + b * 128;
-        for (int kc = 0; kc < kchunks; kc += 2) {
-          mbar_wait(&ctl->full[s], ph);                    // the Z_I stage (two chunks)
+      int gc = 0;                                          // running group counter over all items of this pair
+      int itn = 0;                                         // running item counter
+      for (int item = pair; item < p.items; item += npairs, ++itn) {
+        const SweepItem it = sweep_item(p, item);
+        auto issue_S = [&](int c) {                        // c: running index of the group
+          const int b = c & 1;
+          const uint32_t u = (uint32_t)(c >> 1);
+          mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
           tc_fence_after();
-          const int sa = s;
-          const uint32_t a_st = ring_addr + s * P2_STAGE;
-          next();
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(&ctl->full[s], ph);                  // the Z_J chunk
+          const uint32_t d_tmem = tmem_s + b * 128;
+          for (int kc = 0; kc < kchunks; kc += 2) {
+            mbar_wait(&ctl->full[s], ph);                    // the Z_I stage (two chunks)
             tc_fence_after();
-            const uint64_t a_d = make_kmajor_sw128_desc(a_st + h * P2_CHUNK);
-            const uint64_t b_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
-              const uint64_t adv = (uint64_t)(k * 2);
-              if (S16)
-                mma_f16_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
-              else
-                mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
-            }
-            if (h == 1) mma_commit_pair_elect(&ctl->empty[sa]);
-            mma_commit_pair_elect(&ctl->empty[s]);
+            const int sa = s;
+            const uint32_t a_st = ring_addr + s * P2_STAGE;
             next();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              mbar_wait(&ctl->full[s], ph);                  // the Z_J chunk
+              tc_fence_after();
+              const uint64_t a_d = make_kmajor_sw128_desc(a_st + h * P2_CHUNK);
+              const uint64_t b_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
+                const uint64_t adv = (uint64_t)(k * 2);
+                if (S16)
+                  mma_f16_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
+                else
+                  mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
+              }
+              if (h == 1) mma_commit_pair_elect(&ctl->empty[sa]);
+              mma_commit_pair_elect(&ctl->empty[s]);
+              next();
+            }
           }
+          mma_commit_pair_elect(&ctl->s_full[b]);
+        };
+        auto issue_P = [&](int g, int c) {                 // g: group inside the item, c: running index
+          const int gb = c % GB;
+          const uint32_t gu = (uint32_t)(c / GB);
+          mbar_wait_cluster(&ctl->g_full[gb], gu & 1);
+          tc_fence_after();
+          for (int t = 0; t < it.ntile; ++t)
+            for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
+              mbar_wait(&ctl->full[s], ph);
+              tc_fence_after();
+              const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+              const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + a8 * P2_CHUNK);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
+                const uint64_t adv = (uint64_t)(k * 2);
+                if (H16)
+                  mma_f16_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
+                                        (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+                else
+                  mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
+                                         (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+              }
+              mma_commit_pair_elect(&ctl->empty[s]);
+              next();
+            }
+          mma_commit_pair_elect(&ctl->g_empty[gb]);
+        };
+        issue_S(gc);
+        for (int g = 0; g < it.ng; ++g) {
+          if (g + 1 < it.ng) issue_S(gc + g + 1);
+          if (g == 0 && itn > 0) {                         // the previous item's dZ^T has been read out of TMEM
+            mbar_wait_cluster(&ctl->dz_empty, (uint32_t)((itn - 1) & 1));
+            tc_fence_after();
+          }
+          issue_P(g, gc + g);
         }
-        mma_commit_pair_elect(&ctl->s_full[b]);
-      };
-      auto issue_P = [&](int g) {
-        const int gb = g % GB;
-        const uint32_t gu = (uint32_t)(g / GB);
-        mbar_wait_cluster(&ctl->g_full[gb], gu & 1);
-        tc_fence_after();
-        for (int t = 0; t < ntile; ++t)
-          for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
-            mbar_wait(&ctl->full[s], ph);
-            tc_fence_after();
-            const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-            const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + a8 * P2_CHUNK);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
-              const uint64_t adv = (uint64_t)(k * 2);
-              if (H16)
-                mma_f16_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
-                                      (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
-              else
-                mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
-                                       (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
-            }
-            mma_commit_pair_elect(&ctl->empty[s]);
-            next();
-          }
-        mma_commit_pair_elect(&ctl->g_empty[gb]);
-      };
-      issue_S(0);
-      for (int g = 0; g < nG; ++g) {
-        if (g + 1 < nG) issue_S(g + 1);
-        issue_P(g);
+        gc += it.ng;
+        mma_commit_pair_elect(&ctl->dz_full);
       }
-      mma_commit_pair_elect(&ctl->dz_full);
     }
   } else {
     // ===================== epilogue (both CTAs): S -> G for this CTA's 64 rows x 256 columns =====================
@@ -2042,20 +2078,16 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const int r = tl & 63;                   // row of this CTA's 64-row slice
     const int jh = tl >> 6;                  // lanes 64..127 hold columns 128..255 of the same rows (2x2 layout)
     const int j0 = jh * 128 + cq * 32;       // first of this thread's 32 columns inside a group
-    const int gi = row_base + (int)rank * 64 + r;
 
-    const double sum_r = FUSED ? p.acc[2] : 0.0;
-    const float sigma0 = FUSED ? (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
-    const float cval = FUSED ? 0.f : p.stats[EDRL_MMD_STAT_C];
+    const double sum_r = p.acc[2];
+    const float sigma0 = (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num);
     float sig_last = sigma0;
     for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
     const float negc_last = -LOG2E / sig_last;
     if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
-
-    const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
-    const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
     const uint32_t s_empty_leader0 = mapa_u32(smem_u32(&ctl->s_empty[0]), 0);
     const uint32_t g_full_leader0 = mapa_u32(smem_u32(&ctl->g_full[0]), 0);
+    const uint32_t dz_empty_leader = mapa_u32(smem_u32(&ctl->dz_empty), 0);
     // H16: |G'| <= (sum_k mul^-k) / (sigma_0 min(n_s, n_t)^2); scale by 2^eg so that it stays below 2^14
     float gs = 1.f, gs_inv = 1.f;
     if (H16) {
@@ -2070,252 +2102,213 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       gs = ldexpf(1.f, 14 - ex);
       gs_inv = ldexpf(1.f, ex - 14);
     }
-    const float rc = (-ai / sigma0) * gs;                   // G'_ij 2^eg = (a_j Q_ij) rc
-    const bool count_row = FUSED && ypass == 0 && (gi - rng_begin) < rng_count && gi < p.n;
-    const float ai_m = count_row ? ai : 0.f;
-    double accM = 0.0, accD = 0.0;
     // S16: the tensor core saw Z 2^e on both sides: S = 2^(2e) z_i . z_j
     const float m2s = S16 ? -ldexpf(2.f, -2 * p.fscale[p.d_pad]) : -2.f;
-    float rowsum = 0.f;                                     // of the rounded G values, in units of 2^-eg
+    double accM = 0.0, accD = 0.0;
+    int gc = 0, itn = 0;
 
-    // (r_j, a_j) of the next group: fetched one group ahead by the first 256 epilogue threads
-    float nxt_r = 0.f, nxt_a = 0.f;
-    if (et < Q_GROUP) {
-      nxt_r = (float)p.racc[g_begin * Q_GROUP + et];
-      nxt_a = p.a[g_begin * Q_GROUP + et];
-    }
+    for (int item = pair; item < p.items; item += npairs, ++itn) {
+      const SweepItem it = sweep_item(p, item);
+      const int gi = it.row_base + (int)rank * 64 + r;
+      const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
+      const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
+      const float rc = (-ai / sigma0) * gs;                   // G'_ij 2^eg = (a_j Q_ij) rc
+      const bool count_row = it.ypass == 0 && (gi - it.rng_begin) < it.rng_count && gi < p.n;
+      const float ai_m = count_row ? ai : 0.f;
+      float rowsum = 0.f;                                     // of the rounded G values, in units of 2^-eg
+      float2 tM2 = make_float2(0.f, 0.f), tD2 = make_float2(0.f, 0.f);   // this row's forward sums over the item
+      float tMs = 0.f, tDs = 0.f;                             // (generic kernel_mul / kernel_num path)
 
-    for (int g = 0; g < nG; ++g) {
-      const int b = g & 1;
-      const uint32_t u = (uint32_t)(g >> 1);
-      const int gb = g % GB;
-      const uint32_t gu = (uint32_t)(g / GB);
+      // (r_j, a_j) of the next group: fetched one group ahead by the first 256 epilogue threads and parked in
+      // registers unconverted, so that nothing waits for the load before the next group starts
+      double nxt_r = 0.0;
+      float nxt_a = 0.f;
       if (et < Q_GROUP) {
-        ctl->col_r[b][et] = nxt_r;
-        ctl->col_a[b][et] = nxt_a;
-        if (g + 1 < nG) {
-          nxt_r = (float)p.racc[(g_begin + g + 1) * Q_GROUP + et];
-          nxt_a = p.a[(g_begin + g + 1) * Q_GROUP + et];
-        }
+        nxt_r = p.racc[it.g_begin * Q_GROUP + et];
+        nxt_a = p.a[it.g_begin * Q_GROUP + et];
       }
-      named_barrier_sync(1, SW_EPI_THREADS);
-      mbar_wait(&ctl->s_full[b], u & 1);
-      tc_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + cq * 32), v);
-      tmem_ld_wait();
-      // the S stage is free as soon as its values sit in registers
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(s_empty_leader0 + 8u * (uint32_t)b);
-      uint32_t gp[H16 ? 16 : 32];                            // packed binary16 pairs / TF32 words of this row's G
-      const float4 *cr4 = reinterpret_cast<const float4 *>(&ctl->col_r[b][j0]);
-      const float4 *ca4 = reinterpret_cast<const float4 *>(&ctl->col_a[b][j0]);
-      if (FAST) {
-        float2 tM2 = make_float2(0.f, 0.f), tD2 = make_float2(0.f, 0.f);
-        const float2 ri2 = make_float2(ri, ri), m2s2 = make_float2(m2s, m2s), nc2 = make_float2(negc_last, negc_last);
-        const float2 half2c = make_float2(0.5f, 0.5f), rc2 = make_float2(rc, rc);
+
+      for (int g = 0; g < it.ng; ++g, ++gc) {
+        const int b = gc & 1;
+        const uint32_t u = (uint32_t)(gc >> 1);
+        const int gb = gc % GB;
+        const uint32_t gu = (uint32_t)(gc / GB);
+        if (et < Q_GROUP) {
+          ctl->col_r[b][et] = (float)nxt_r;
+          ctl->col_a[b][et] = nxt_a;
+          if (g + 1 < it.ng) {
+            nxt_r = p.racc[(it.g_begin + g + 1) * Q_GROUP + et];
+            nxt_a = p.a[(it.g_begin + g + 1) * Q_GROUP + et];
+          }
+        }
+        named_barrier_sync(1, SW_EPI_THREADS);
+        mbar_wait(&ctl->s_full[b], u & 1);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 128 + cq * 32), v);
+        tmem_ld_wait();
+        // the S stage is free as soon as its values sit in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(s_empty_leader0 + 8u * (uint32_t)b);
+        uint32_t gp[H16 ? 16 : 32];                            // packed binary16 pairs / TF32 words of this row's G
+        const float4 *cr4 = reinterpret_cast<const float4 *>(&ctl->col_r[b][j0]);
+        const float4 *ca4 = reinterpret_cast<const float4 *>(&ctl->col_a[b][j0]);
+        if (FAST) {
+          const float2 ri2 = make_float2(ri, ri), m2s2 = make_float2(m2s, m2s), nc2 = make_float2(negc_last, negc_last);
+          const float2 half2c = make_float2(0.5f, 0.5f), rc2 = make_float2(rc, rc);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 rj = cr4[q], aj = ca4[q];
+          for (int q = 0; q < 8; ++q) {
+            const float4 rj = cr4[q], aj = ca4[q];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int j = q * 4 + hh * 2;
-            const float2 rj2 = hh ? make_float2(rj.z, rj.w) : make_float2(rj.x, rj.y);
-            const float2 aj2 = hh ? make_float2(aj.z, aj.w) : make_float2(aj.x, aj.y);
-            const float2 s2 = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-            const float2 lraw = fma2(m2s2, s2, add2(ri2, rj2));
-            const float2 L = make_float2(fmaxf(lraw.x, 0.f), fmaxf(lraw.y, 0.f));
-            const float2 t = mul2(L, nc2);
-            const float2 e4 = make_float2(ex2_approx(t.x), ex2_approx(t.y));
-            const float2 e3 = mul2(e4, e4);
-            const float2 e2 = mul2(e3, e3);
-            const float2 e1 = mul2(e2, e2);
-            const float2 e0 = mul2(e1, e1);
-            const float2 Q = fma2(fma2(fma2(fma2(e4, half2c, e3), half2c, e2), half2c, e1), half2c, e0);
-            const float2 aQ = mul2(aj2, Q);
-            if (FUSED) {
+            for (int hh = 0; hh < 2; ++hh) {
+              const int j = q * 4 + hh * 2;
+              const float2 rj2 = hh ? make_float2(rj.z, rj.w) : make_float2(rj.x, rj.y);
+              const float2 aj2 = hh ? make_float2(aj.z, aj.w) : make_float2(aj.x, aj.y);
+              const float2 s2 = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              const float2 lraw = fma2(m2s2, s2, add2(ri2, rj2));
+              const float2 L = make_float2(fmaxf(lraw.x, 0.f), fmaxf(lraw.y, 0.f));
+              const float2 t = mul2(L, nc2);
+              const float2 e4 = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+              const float2 e3 = mul2(e4, e4);
+              const float2 e2 = mul2(e3, e3);
+              const float2 e1 = mul2(e2, e2);
+              const float2 e0 = mul2(e1, e1);
+              const float2 Q = fma2(fma2(fma2(fma2(e4, half2c, e3), half2c, e2), half2c, e1), half2c, e0);
+              const float2 aQ = mul2(aj2, Q);
               const float2 K = add2(add2(add2(e0, e1), add2(e2, e3)), e4);
               tM2 = fma2(aj2, K, tM2);
               tD2 = fma2(aQ, L, tD2);
+              // the clamp mask [L_raw >= 0] is not applied to G: a pair with L_raw < 0 is a numerical duplicate
+              // (z_i = z_j up to rounding), whose term G_ij (z_i - z_j) vanishes whatever G_ij is
+              const float2 gv = mul2(aQ, rc2);
+              if (H16) {
+                const uint32_t pk = pack_half2(gv.x, gv.y);
+                gp[j >> 1] = pk;
+                rowsum = add_half2_f32(rowsum, pk);
+              } else {
+                const float g0 = to_tf32(gv.x), g1 = to_tf32(gv.y);
+                gp[j] = __float_as_uint(g0);
+                gp[j + 1] = __float_as_uint(g1);
+                rowsum += g0 + g1;
+              }
             }
-            // the clamp mask [L_raw >= 0] is not applied to G: a pair with L_raw < 0 is a numerical duplicate
-            // (z_i = z_j up to rounding), whose term G_ij (z_i - z_j) vanishes whatever G_ij is
-            float2 gv = mul2(aQ, rc2);
-            if (!FUSED) {
-              gv.x += (aj2.x != 0.f && lraw.x >= 0.f) ? cval : 0.f;
-              gv.y += (aj2.y != 0.f && lraw.y >= 0.f) ? cval : 0.f;
-            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float rj = ctl->col_r[b][j0 + j], aj = ctl->col_a[b][j0 + j];
+            const float Lraw = fmaf(m2s, __uint_as_float(v[j]), ri + rj);
+            const float L = fmaxf(Lraw, 0.f);
+            float K, Q;
+            kernel_terms<false>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
+            tMs = fmaf(aj, K, tMs);
+            tDs = fmaf(aj * L, Q, tDs);
+            const float gv = (aj * Q) * rc;
             if (H16) {
-              const uint32_t pk = pack_half2(gv.x, gv.y);
-              gp[j >> 1] = pk;
-              rowsum = add_half2_f32(rowsum, pk);
+              const __half hv = __float2half_rn(gv);
+              const uint32_t hb = (uint32_t)__half_as_ushort(hv);
+              if (j & 1) gp[j >> 1] |= hb << 16; else gp[j >> 1] = hb;
+              rowsum += __half2float(hv);
             } else {
-              const float g0 = to_tf32(gv.x), g1 = to_tf32(gv.y);
+              const float g0 = to_tf32(gv);
               gp[j] = __float_as_uint(g0);
-              gp[j + 1] = __float_as_uint(g1);
-              rowsum += g0 + g1;
+              rowsum += g0;
             }
           }
         }
-        if (FUSED) {
-          accM += (double)(ai_m * (tM2.x + tM2.y));
-          accD += (double)(ai_m * (tD2.x + tD2.y));
+        // ---- G row segment -> shared memory (K-major, 128-byte swizzle), once P(g - GB) has consumed the buffer ----
+        mbar_wait(&ctl->g_empty[gb], (gu & 1) ^ 1);
+        uint8_t *gbuf = g_smem + gb * Cfg::G_BYTES;
+        if (H16) {
+          // 32 halfs = 64 bytes = four 16-byte chunks of row r in K-atom (j0 / 64)
+          uint8_t *atom = gbuf + (j0 >> 6) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+          const int cb = (j0 & 63) >> 3;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) =
+                make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
+        } else {
+          uint8_t *atom = gbuf + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            *reinterpret_cast<uint4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
+                make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
         }
-      } else {
-        float tM = 0.f, tD = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float rj = ctl->col_r[b][j0 + j], aj = ctl->col_a[b][j0 + j];
-          const float Lraw = fmaf(m2s, __uint_as_float(v[j]), ri + rj);
-          const float L = fmaxf(Lraw, 0.f);
-          float K, Q;
-          kernel_terms<false>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
-          if (FUSED) {
-            tM = fmaf(aj, K, tM);
-            tD = fmaf(aj * L, Q, tD);
-          }
-          float gv = (aj * Q) * rc;
-          if (!FUSED) gv += (aj != 0.f && Lraw >= 0.f) ? cval : 0.f;
-          if (H16) {
-            const __half hv = __float2half_rn(gv);
-            const uint32_t hb = (uint32_t)__half_as_ushort(hv);
-            if (j & 1) gp[j >> 1] |= hb << 16; else gp[j >> 1] = hb;
-            rowsum += __half2float(hv);
-          } else {
-            const float g0 = to_tf32(gv);
-            gp[j] = __float_as_uint(g0);
-            rowsum += g0;
-          }
-        }
-        if (FUSED) {
-          accM += (double)(ai_m * tM);
-          accD += (double)(ai_m * tD);
-        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(g_full_leader0 + 8u * (uint32_t)gb);
       }
-      // ---- G row segment -> shared memory (K-major, 128-byte swizzle), once P(g - GB) has consumed the buffer ----
-      mbar_wait(&ctl->g_empty[gb], (gu & 1) ^ 1);
-      uint8_t *gbuf = g_smem + gb * Cfg::G_BYTES;
-      if (H16) {
-        // 32 halfs = 64 bytes = four 16-byte chunks of row r in K-atom (j0 / 64)
-        uint8_t *atom = gbuf + (j0 >> 6) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
-        const int cb = (j0 & 63) >> 3;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) =
-              make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
-      } else {
-        uint8_t *atom = gbuf + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          *reinterpret_cast<uint4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
-              make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(g_full_leader0 + 8u * (uint32_t)gb);
-    }
-    if (FUSED && ypass == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        accM += __shfl_xor_sync(0xffffffffu, accM, o);
-        accD += __shfl_xor_sync(0xffffffffu, accD, o);
-      }
-      if (lane == 0) {
-        ctl->red[ew][0] = accM;
-        ctl->red[ew][1] = accD;
-      }
+      // ---- end of the item: forward sums, row sums of G, write-out ----
+      accM += (double)(ai_m * ((tM2.x + tM2.y) + tMs));
+      accD += (double)(ai_m * ((tD2.x + tD2.y) + tDs));
+      ctl->part[jh * 4 + cq][r] = rowsum * gs_inv;
       named_barrier_sync(1, SW_EPI_THREADS);
-      if (et == 0) {
-        double m = 0.0, dd = 0.0;
+      if (et < 64) {
+        // 8 partials per row (2 lane halves x 4 column chunks) -> rowsum(G')_i of this item's columns, for apply_grad
+        float tot = 0.f;
 #pragma unroll
-        for (int k = 0; k < SW_EPI_WARPS; ++k) {
-          m += ctl->red[k][0];
-          dd += ctl->red[k][1];
-        }
-        atomicAdd(p.acc + 0, m);
-        atomicAdd(p.acc + 1, dd);
-        __threadfence();
-        const unsigned t = atomicAdd(p.ticket, 1u);
-        if (t == (unsigned)p.ticket_total - 1u) {
-          __threadfence();
-          const double Mv = atomicAdd(p.acc + 0, 0.0);
-          const double Ds = atomicAdd(p.acc + 1, 0.0);
-          if (p.partial) {
-            p.partial[0] = Mv;
-            p.partial[1] = Ds;
-          }
-          if (p.finalize) write_final_stats(Mv, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats_out);
-        }
+        for (int k = 0; k < 8; ++k) tot += ctl->part[k][et];
+        // (only this panel's own rows: rows past the range end may belong to another panel with another split)
+        if ((int)rank * 64 + et < it.rows_here)
+          p.rowsum[(size_t)(it.ypass * SW_MAX_SPLIT + it.slab) * p.n_pad + it.row_base + (int)rank * 64 + et] = tot;
       }
-    }
-    // ---- row sums of G: 8 partials per row (2 lane halves x 4 column chunks) -> all 128 rows in both CTAs ----
-    named_barrier_sync(1, SW_EPI_THREADS);
-    float *part = &ctl->col_r[0][0];                       // [8][64] (col_r[0..1] are contiguous)
-    float *rs_all = ctl->rs_all;
-    part[(jh * 4 + cq) * 64 + r] = rowsum * gs_inv;
-    named_barrier_sync(1, SW_EPI_THREADS);
-    if (et < 64) {
-      float tot = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot += part[k * 64 + et];
-      rs_all[rank * 64 + et] = tot;
-      st_cluster_f32(mapa_u32(smem_u32(&rs_all[rank * 64 + et]), rank ^ 1u), tot);
-    }
-  }
-  __syncwarp();
-  cluster_sync_all();
-
-  if (warp >= 2) {
-    // ===================== write-out: dZ[i, f] = coef (rowsum_i z_i[f] - dZ^T[f, i]) =====================
-    const int ew = warp - 2;
-    const int lg = warp & 3;
-    const int cq = ew >> 2;
-    const int tl = lg * 32 + lane;
-    const float *rs_all = ctl->rs_all;
-    float coef = 1.f;
-    if (!FUSED) {
-      const float M = p.stats[EDRL_MMD_STAT_M];
-      const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
-      coef = 4.f * sgn * p.grad_out[0];
-    }
-    int rows_here = rng_count - lpanel * BM;
-    if (rows_here > BM) rows_here = BM;
-    if (p.n - row_base < rows_here) rows_here = p.n - row_base;
-    mbar_wait(&ctl->dz_full, 0);
-    tc_fence_after();
-    float gs_inv = 1.f;                                       // H16: undo the scale of G (same formula as above)
-    if (H16) {
-      const float sigma0 = FUSED ? (float)bandwidth_sigma0(p.acc[2], p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
-      float qmax = 0.f, wk = 1.f;
-      for (int k = 0; k < p.num; ++k) {
-        qmax += wk;
-        wk /= p.mul;
-      }
-      const float nmin = (float)min(p.n_s, p.n_t);
-      int ex = 0;
-      frexpf(qmax / (sigma0 * nmin * nmin), &ex);
-      gs_inv = ldexpf(1.f, ex - 14);
-    }
-    const int i0 = cq * 32;
-    if (i0 < rows_here) {
-      for (int t = 0; t < ntile; ++t) {
-        const int f = f0 + t * 256 + (int)rank * 128 + tl;
+      // U[slab][i, f] = -(G' Z)_i[f] of this item's columns (rowsum_i z_i is added by edrl_mmd_apply_grad)
+      mbar_wait(&ctl->dz_full, (uint32_t)(itn & 1));
+      tc_fence_after();
+      const int i0 = cq * 32;
+      for (int t = 0; t < it.ntile; ++t) {
+        const int f = it.f0 + t * 256 + (int)rank * 128 + tl;
         const bool f_ok = f < p.d;
-        const float unscale = (H16 && f_ok) ? ldexpf(gs_inv, -p.fscale[f]) : 1.f;     // and of column f of Z^T
+        const float unscale = (H16 && f_ok) ? -ldexpf(gs_inv, -p.fscale[f]) : -1.f;     // also of column f of Z^T
         uint32_t v[32];
         tmem_ld_32x32(tmem_dz + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BN + i0), v);
         tmem_ld_wait();
-        if (f_ok) {
-          const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
-          float *oc = p.dz + ((size_t)slab * (p.row_count + p.row_count2) + out_row0 + i0) * p.d + f;
+        if (t == it.ntile - 1) {                              // the accumulators may be overwritten by the next item
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(dz_empty_leader);
+        }
+        if (f_ok && i0 < it.rows_here) {
+          float *oc = p.dz + ((size_t)it.slab * (p.row_count + p.row_count2) + it.out_row0 + i0) * p.d + f;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (i0 + j < rows_here)
-              oc[(size_t)j * p.d] =
-                  coef * fmaf(rs_all[i0 + j], zc[(size_t)j * p.d_pad], -(__uint_as_float(v[j]) * unscale));
+            if (i0 + j < it.rows_here) oc[(size_t)j * p.d] = __uint_as_float(v[j]) * unscale;
           }
         }
+      }
+    }
+    // ---- forward sums of this CTA -> global accumulators; the last CTA finalises ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      accM += __shfl_xor_sync(0xffffffffu, accM, o);
+      accD += __shfl_xor_sync(0xffffffffu, accD, o);
+    }
+    if (lane == 0) {
+      ctl->red[ew][0] = accM;
+      ctl->red[ew][1] = accD;
+    }
+    named_barrier_sync(1, SW_EPI_THREADS);
+    if (et == 0) {
+      double m = 0.0, dd = 0.0;
+#pragma unroll
+      for (int k = 0; k < SW_EPI_WARPS; ++k) {
+        m += ctl->red[k][0];
+        dd += ctl->red[k][1];
+      }
+      atomicAdd(p.acc + 0, m);
+      atomicAdd(p.acc + 1, dd);
+      __threadfence();
+      const unsigned t = atomicAdd(p.ticket, 1u);
+      if (t == gridDim.x - 1) {
+        __threadfence();
+        const double Mv = atomicAdd(p.acc + 0, 0.0);
+        const double Ds = atomicAdd(p.acc + 1, 0.0);
+        if (p.partial) {
+          p.partial[0] = Mv;
+          p.partial[1] = Ds;
+        }
+        if (p.finalize) write_final_stats(Mv, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats_out);
       }
     }
   }
@@ -2335,8 +2328,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(128)
 mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const double *__restrict__ colsum_hi,
                       const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
-                      int row_begin2, int row_count2, int d, int d_pad, int n, int panels, int full_items, int split,
-                      float *__restrict__ dz) {
+                      int row_begin2, int row_count2, int d, int d_pad, int n, int n_pad, int panels, int full_items,
+                      int split, const float *__restrict__ rowsum, float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
@@ -2352,26 +2345,35 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
   const int panel = (r < row_count) ? r / BM : (row_count + BM - 1) / BM + (r - row_count) / BM;
   if (VEC4) {
     for (int f = (blockIdx.y * 128 + threadIdx.x) * 4; f < d; f += gridDim.y * 512) {
-      const int nslab = ((f / P2_FEATS) * panels + panel < full_items) ? 1 : split;
+      const int yp = f / P2_FEATS;
+      const int nslab = (yp * panels + panel < full_items) ? 1 : split;
       float4 u = *reinterpret_cast<const float4 *>(ur + f);
+      float rs = rowsum[(size_t)(yp * 8) * n_pad + gr];
       for (int sl = 1; sl < nslab; ++sl) {
         const float4 w = *reinterpret_cast<const float4 *>(ur + sl * slab + f);
         u.x += w.x; u.y += w.y; u.z += w.z; u.w += w.w;
+        rs += rowsum[(size_t)(yp * 8 + sl) * n_pad + gr];
       }
+      const float zc = fmaf(cv, fn, rs);                      // (rowsum(G')_i + c n) z_i
       const float4 z = __ldg(reinterpret_cast<const float4 *>(zr + f));
       float4 o;
-      o.x = coef * fmaf(cv, fmaf(fn, z.x, -(float)colsum_hi[f + 0]), u.x);
-      o.y = coef * fmaf(cv, fmaf(fn, z.y, -(float)colsum_hi[f + 1]), u.y);
-      o.z = coef * fmaf(cv, fmaf(fn, z.z, -(float)colsum_hi[f + 2]), u.z);
-      o.w = coef * fmaf(cv, fmaf(fn, z.w, -(float)colsum_hi[f + 3]), u.w);
+      o.x = coef * (fmaf(zc, z.x, -cv * (float)colsum_hi[f + 0]) + u.x);
+      o.y = coef * (fmaf(zc, z.y, -cv * (float)colsum_hi[f + 1]) + u.y);
+      o.z = coef * (fmaf(zc, z.z, -cv * (float)colsum_hi[f + 2]) + u.z);
+      o.w = coef * (fmaf(zc, z.w, -cv * (float)colsum_hi[f + 3]) + u.w);
       *reinterpret_cast<float4 *>(orow + f) = o;
     }
   } else {
     for (int f = blockIdx.y * 128 + threadIdx.x; f < d; f += gridDim.y * 128) {
-      const int nslab = ((f / P2_FEATS) * panels + panel < full_items) ? 1 : split;
+      const int yp = f / P2_FEATS;
+      const int nslab = (yp * panels + panel < full_items) ? 1 : split;
       float u = ur[f];
-      for (int sl = 1; sl < nslab; ++sl) u += ur[sl * slab + f];
-      dz[(size_t)r * d + f] = coef * fmaf(cv, fmaf(fn, __ldg(zr + f), -(float)colsum_hi[f]), u);
+      float rs = rowsum[(size_t)(yp * 8) * n_pad + gr];
+      for (int sl = 1; sl < nslab; ++sl) {
+        u += ur[sl * slab + f];
+        rs += rowsum[(size_t)(yp * 8 + sl) * n_pad + gr];
+      }
+      dz[(size_t)r * d + f] = coef * (fmaf(fmaf(cv, fn, rs), __ldg(zr + f), -cv * (float)colsum_hi[f]) + u);
     }
   }
 }
@@ -2388,10 +2390,10 @@ static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt
   return 0;
 }
 
-template <bool FAST, bool FUSED, int MODE = 0>
+template <bool FAST, int MODE = 0>
 static int launch_sweep256_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z128, const CUtensorMap &tm_zt,
                              const BwdParams &p, dim3 grid, cudaStream_t st) {
-  auto kern = mmd_sweep256_kernel<FAST, FUSED, MODE>;
+  auto kern = mmd_sweep256_kernel<FAST, MODE>;
   constexpr int SMEM = SweepCfg<MODE>::SMEM_BYTES;
   EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   kern<<<grid, SW_THREADS, SMEM, st>>>(tm_z64, tm_z128, tm_zt, p);
@@ -2409,8 +2411,8 @@ struct SweepPlan {
   int vpanels;      // panels x feature passes
   int full_items;   // virtual panels swept whole
   int split;        // column slabs of every later virtual panel (1, 2, 4 or 8)
-  int items;        // CTA pairs to launch
-  int items_pass0;  // of which belong to feature pass 0 (they carry the forward sums)
+  int items;        // work items (whole or slab sweeps of a virtual panel)
+  int pairs;        // persistent CTA pairs to launch: pair c takes items c, c + pairs, ...
 };
 
 static SweepPlan make_plan(const Layout &L, int row_count, int row_count2) {
@@ -2439,8 +2441,7 @@ static SweepPlan make_plan(const Layout &L, int row_count, int row_count2) {
   }
   if (pl.split == 1) pl.full_items = pl.vpanels;
   pl.items = pl.full_items + (pl.vpanels - pl.full_items) * pl.split;
-  const int full0 = pl.full_items < pl.panels ? pl.full_items : pl.panels;
-  pl.items_pass0 = full0 + (pl.panels - full0) * pl.split;
+  pl.pairs = pl.items < C ? pl.items : C;
   return pl;
 }
 
@@ -2583,8 +2584,9 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   p.partial = partial; p.loss = loss; p.stats_out = stats;
   p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
   const SweepPlan pl = make_plan(L, row_count, row_count2);
-  p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.ticket_total = 2 * pl.items_pass0;
-  dim3 grid2(2 * pl.items, 1, 1);
+  p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.items = pl.items;
+  p.rowsum = reinterpret_cast<float *>(ws + L.off_rowsum);
+  dim3 grid2(2 * pl.pairs, 1, 1);
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
   if (L.h16) {
@@ -2595,18 +2597,18 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
       CUtensorMap tm_z64h;
       if (int rc = make_tmap_2d_f16(&tm_z64h, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 64, 64)) return rc;
       if (int rc = make_tmap_2d_f16(&tm_z128, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 128, 64)) return rc;
-      if (fast) return launch_sweep256_t<true, true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
-      return launch_sweep256_t<false, true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+      if (fast) return launch_sweep256_t<true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+      return launch_sweep256_t<false, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
     }
     if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
-    if (fast) return launch_sweep256_t<true, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-    return launch_sweep256_t<false, true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    if (fast) return launch_sweep256_t<true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    return launch_sweep256_t<false, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
   }
   {
     CUtensorMap tm_z128;
     if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
-    if (fast) return launch_sweep256_t<true, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-    return launch_sweep256_t<false, true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+    if (fast) return launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+    return launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
   }
 }
 
@@ -2627,10 +2629,12 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
   if (v4)
     mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                      row_count2, d, L.d_pad, L.n, pl.panels, pl.full_items, pl.split, dZ);
+                                                      row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split,
+        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   else
     mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                       row_count2, d, L.d_pad, L.n, pl.panels, pl.full_items, pl.split, dZ);
+                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split,
+        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   EDRL_LAUNCHED();
   return 0;
 }
