@@ -619,7 +619,7 @@ def run_ours(args, rank, local_rank, world):
                     "achieved": ach_f, "frac": ach_f / peak, "algorithmic_flops": flops_f}
         bwd_info = {"kernel": "mmd_bwd_pair_kernel (separate tile-recomputing backward)", "ms": b_ms,
                     "achieved": ach_b, "frac": ach_b / peak, "algorithmic_flops": flops_b}
-        if prec in ("tf32", "tf32h"):
+        if prec in ("tf32", "tf32h", "f16s"):
             # the training step's dominant launch: forward sums + gradient in one sweep over the Gram tiles
             g_ms = timed_steps(fused_only, reps, 2, flush, 1) / reps
             flops_g = flops_f + flops_b
@@ -627,16 +627,22 @@ def run_ours(args, rank, local_rank, world):
             if prec == "tf32h":
                 # Gram at the kind::tf32 rate, G.Z at the kind::f16 rate (twice as fast): blended peak for 1 : 2 work
                 peak = flops_g / (flops_f / peak + flops_b / (2.0 * peak))
-            roof = {"bound": "tensor", "kernel": "mmd_sweep256_kernel<FUSED> (forward sums + gradient, one Gram sweep)",
+            elif prec == "f16s":
+                peak = peaks["bf16_burst"]            # both contractions issue kind::f16 MMAs
+            mode_id = {"tf32": 0, "tf32h": 1, "f16s": 2}[prec]
+            roof = {"bound": "tensor",
+                    "kernel": f"mmd_sweep256_kernel<FAST, MODE={mode_id}> (forward sums + gradient, one persistent Gram sweep)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": (profiled_traffic("mmd_sweep256_kernel<1, 1>") if (N, d) == (8192, 512) else None),
+                    "traffic": (profiled_traffic(f"mmd_sweep256_kernel<1, {mode_id}>") if (N, d) == (8192, 512) else None),
                     "traffic_note": "DRAM bytes per launch (ncu, profiles/); algorithmic HBM bytes are 3 n d 4 = 96 MiB "
                                     "(read Z and Z^T, write U) -- the kernel is bound by L2 -> SM traffic, not DRAM",
                     "ms": g_ms,
                     "ms_includes": "the two prep kernels (~0.06 ms at N=8192) launched by the same C-ABI call",
-                    "peak_source": (f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)" if prec == "tf32" else
-                                    f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s: Gram (1/3 of the work) at the "
-                                    "TF32 rate (/2), G.Z (2/3) at the f16 rate"),
+                    "peak_source": {
+                        "tf32": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)",
+                        "tf32h": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s: Gram (1/3 of the work) at the "
+                                 "TF32 rate (/2), G.Z (2/3) at the f16 rate",
+                        "f16s": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s (kind::f16 MMAs)"}[prec],
                     "algorithmic_flops": flops_g, "mma_per_product": 1,
                     "executed_tensor_flops": (2.0 * n * n * d * passes + 2.0 * n * n * d)}
         else:
@@ -646,7 +652,7 @@ def run_ours(args, rank, local_rank, world):
                     "algorithmic_flops": flops_b, "mma_per_product": mma_per_product,
                     "executed_tensor_flops": (2.0 * n * n * d * math.ceil(d / 256) + 2.0 * n * n * d) * 3}
         if sharded:
-            one = (g_ms + 0.0) if prec in ("tf32", "tf32h") else (f_ms + b_ms)
+            one = (g_ms + 0.0) if prec in ("tf32", "tf32h", "f16s") else (f_ms + b_ms)
             base = {"n_gpus": 1, "ms_per_step": one, "value": N / (one * 1e-3),
                     "note": "same workload, unsharded, on rank 0 alone through the C-ABI (fused pass in TF32 mode; "
                             "the O(nd) apply_grad kernel is not included)"}
@@ -688,8 +694,32 @@ def run_ours(args, rank, local_rank, world):
             line["essence_point"] = extras
             line["sweep_vs_torch_gpu"] = sweep_vs_torch_gpu(prec)
             # the same step in the other precision modes, same timing recipe
-            line["precision_modes"] = {prec: {"ms_per_step": ms_per_step, "value": value}}
-            for other in ("tf32", "tf32h", "3xtf32"):
+            def mode_roofline(o):
+                """fused C-ABI call (prep + sweep) alone in precision mode o: ms, achieved TFLOP/s, its own peak"""
+                if o == "3xtf32":
+                    return {}
+                fl = _flags(o)
+                ws_o = Workspace(N, N, d, fl, dev)
+                nn = 2 * N
+                u_o = torch.empty(int(lib.edrl_mmd_grad_slabs(N, N, d, fl, nn, 0)) * nn, d, device=dev)
+                lo, so = torch.empty((), device=dev), torch.empty(8, device=dev)
+                xo, yo = x.detach(), y.detach()
+                sto = _lib.stream_and_device(xo)
+
+                def call():
+                    _lib.check(lib.edrl_mmd_forward_grad(xo.data_ptr(), yo.data_ptr(), N, N, d, 2.0, 5, fl, 0, nn, 0, 0, 1,
+                                                         lo.data_ptr(), so.data_ptr(), None, u_o.data_ptr(), ws_o.ptr,
+                                                         ws_o.nbytes, sto))
+                t = timed_steps(call, 10, 3, flush, 1) / 10
+                tf32_peak = peaks["bf16_burst"] / 2.0
+                fa = 3.0 * nn * nn * d
+                pk = {"tf32": tf32_peak, "tf32h": 3.0 / (1.0 / tf32_peak + 2.0 / peaks["bf16_burst"]),
+                      "f16s": peaks["bf16_burst"]}[o]
+                return {"fused_call_ms": t, "achieved_tflops": fa / (t * 1e-3) / 1e12, "peak_tflops": pk,
+                        "frac": fa / (t * 1e-3) / 1e12 / pk}
+
+            line["precision_modes"] = {prec: dict(ms_per_step=ms_per_step, value=value, **mode_roofline(prec))}
+            for other in ("tf32", "tf32h", "f16s", "3xtf32"):
                 if other == prec:
                     continue
 
@@ -699,10 +729,12 @@ def run_ours(args, rank, local_rank, world):
                     edrl_b200.MK_MMD(x, y, precision=o).backward()
 
                 t = timed_steps(other_step, 5, 3, flush, 1) / 5
-                line["precision_modes"][other] = {"ms_per_step": t, "value": N / (t * 1e-3)}
+                line["precision_modes"][other] = dict(ms_per_step=t, value=N / (t * 1e-3), **mode_roofline(other))
             line["precision_modes"]["note"] = (
                 "tf32: TF32 Gram and TF32 G.Z (headline). tf32h: same TF32 Gram, G.Z operands stored as scaled "
-                "binary16 with the same 11-bit significands (gradients agree with tf32 to 2e-5 |g|_inf). 3xtf32: hi/lo "
+                "binary16 with the same 11-bit significands (gradients agree with tf32 to 2e-5 |g|_inf). f16s: the Gram "
+                "too reads a scaled binary16 copy of the TF32-rounded operand (identical significands, exact products, "
+                "fp32 accumulation; agrees with tf32 to 2e-6 on the loss and 5e-5 |g|_inf on gradients). 3xtf32: hi/lo "
                 "split, fp32-level accuracy, first-generation kernels.")
             line["essence_path_vs_torch_gpu"] = essence_path_vs_torch_gpu()
             line["eval_missing_modality"] = eval_missing_modality()
@@ -718,7 +750,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32h", "3xtf32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32h", "f16s", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()

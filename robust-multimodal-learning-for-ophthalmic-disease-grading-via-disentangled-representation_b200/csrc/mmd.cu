@@ -177,7 +177,7 @@ prep_center_kernel(const float *__restrict__ X, const float *__restrict__ Y, int
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int cc = wy * 4 + k;
-      zthi[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_hi[lane][cc];
+      if (zthi) zthi[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_hi[lane][cc];
       if (SPLIT3) ztlo[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = tile_lo[lane][cc];
       // the TF32 value has a 10-bit significand already: its scaled binary16 copy is exact (short of underflow)
       if (H16) zt16[(size_t)(ct * 32 + cc) * n_pad + row0 + lane] = __float2half_rn(tile_hi[lane][cc] * s_scale[cc]);
@@ -1635,8 +1635,10 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
 }
 
 // ----------------------------------------------------------------------------- host side
+// need_zt: also write the fp32 transposed copy Z^T (the separate backward and the TF32 sweep read it; the binary16
+// sweeps read Z^T16 instead and skip these n d 4 bytes)
 static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, const Layout &L, uint8_t *ws,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool need_zt = true) {
   EDRL_CUDA_OK(cudaMemsetAsync(ws + L.off_acc, 0, L.zero_bytes, st));
   const int n = L.n;
   double *acc = reinterpret_cast<double *>(ws + L.off_acc);
@@ -1644,7 +1646,7 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
   double *racc = reinterpret_cast<double *>(ws + L.off_r);
   float *a = reinterpret_cast<float *>(ws + L.off_a);
   float *zhi = reinterpret_cast<float *>(ws + L.off_zhi);
-  float *zthi = reinterpret_cast<float *>(ws + L.off_zthi);
+  float *zthi = need_zt ? reinterpret_cast<float *>(ws + L.off_zthi) : nullptr;
   float *zlo = reinterpret_cast<float *>(ws + L.off_zlo);
   float *ztlo = reinterpret_cast<float *>(ws + L.off_ztlo);
   dim3 g1((d + 127) / 128, (n + 63) / 64);
@@ -1652,7 +1654,7 @@ static int run_prep(const float *X, const float *Y, int n_s, int n_t, int d, con
                                          L.h16 ? reinterpret_cast<unsigned *>(ws + L.off_colmax) : nullptr);
   EDRL_LAUNCHED();
   const int rb = L.n_pad / 32;
-  int nsplit = (296 + rb - 1) / rb;
+  int nsplit = (2368 + rb - 1) / rb;                  // >= 16 blocks of 256 threads per SM when the matrix allows it
   if (nsplit < 1) nsplit = 1;
   if (nsplit > L.d_pad / 32) nsplit = L.d_pad / 32;
   dim3 g2(rb, nsplit), b2(32, 8);
@@ -2566,7 +2568,7 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   EDRL_CHECK_ARG(finalize ? (loss && stats) : (partial != nullptr), "MK_MMD forward_grad: null output");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-  if (int rc = run_prep(X, Y, n_s, n_t, d, L, ws, st)) return rc;
+  if (int rc = run_prep(X, Y, n_s, n_t, d, L, ws, st, !L.h16)) return rc;
   CUtensorMap tm_z64, tm_zt;
   if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
   if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
