@@ -422,6 +422,8 @@ struct PlainRows {          // x [R, W], row stride ld
     run = W - j;
     return x + (size_t)r * ld + j;
   }
+  // rows can be read as float4 (topk_vec_kernel)
+  bool vec4_ok() const { return W % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0; }
 };
 struct EssenceRows {        // virtual rows over att [B,C,S]: v < B positives (class y_b), else negatives
   const float *att;
@@ -458,6 +460,7 @@ struct EssenceRows {        // virtual rows over att [B,C,S]: v < B positives (c
     run = S - s;
     return att + ((size_t)b * C + cls) * S + s;
   }
+  bool vec4_ok() const { return S % 4 == 0 && (reinterpret_cast<uintptr_t>(att) & 15) == 0; }
 };
 
 // bitonic sort (descending) of KP (power of two, <= 1024) 64-bit composites in shared memory by NT threads
@@ -794,6 +797,334 @@ topk_warp_radix_kernel(Rows rows, int R, int k, float *__restrict__ vals, int *_
   }
 }
 
+// ----------------------------------------------------------------------------- K7b vectorised warp select
+// One warp per row, uniform row width W (a multiple of 4, rows 16-byte aligned), k <= 128.  Same range-adaptive MSD
+// radix select as topk_warp_radix_kernel, rebuilt around the instruction count (the select is bound by instruction
+// issue / the integer pipe, not by HBM):
+//   * 128-bit loads: lane l holds float4 number i * 32 + l of the row for i < FI (+ one partial iteration);
+//   * the first histogram pass is unpredicated (every key lies in [kmin, kmax]; lanes without data in the partial
+//     iteration count into a dummy bin), 4 instructions per element;
+//   * the boundary bucket of that pass normally holds a handful of keys: they are collected (lane-local lists, one
+//     warp prefix) and ranked against each other with shuffles, instead of a second and third histogram pass over the
+//     whole row; more than 32 candidates (peaked rows) fall back to further histogram passes;
+//   * winners are compacted LANE-LOCALLY (count, one warp prefix over the 32 lane totals, predicated stores) instead of
+//     one ballot + two popcounts per element -- the unsorted output order is by lane, which edrl_topk_rows(sorted = 0)
+//     leaves unspecified; boundary ties (fewer wanted than present at the threshold key) take a ballot path that
+//     keeps the lowest indices;
+//   * SORTED: the winners (key | ~index composites in shared memory) go through the register bitonic network.
+// FI: full iterations (W / 128), PARTIAL: one more with lanes < (W / 4) % 32.
+constexpr int TV_HIST = 260;                  // 256 bins + dummy bin (16-byte aligned rows)
+constexpr int TV_CSTRIDE = 33;                // words per lane of the candidate staging area (at most 32 candidates; odd: conflict free)
+template <int FI, bool PARTIAL, bool SORTED, class Rows>
+__global__ void __launch_bounds__(128)
+topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
+  constexpr int NI = FI + (PARTIAL ? 1 : 0);
+  constexpr int E = NI * 4;
+  __shared__ __align__(16) unsigned int s_hist[4][TV_HIST];  // per warp: histogram, later 128 64-bit winners
+  __shared__ unsigned int s_cand[4][32 * TV_CSTRIDE];        // per warp: lane-local candidate lists, then the compact list
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + wib;
+  if (r >= R) return;
+  unsigned int *hist = s_hist[wib];
+  uint2 *buf = reinterpret_cast<uint2 *>(hist);              // .x = ~index, .y = key  (little-endian key|~index)
+  const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(hist);
+  const typename Rows::Cursor cur = rows.cursor(r);
+  const bool pvalid = PARTIAL && lane < ((W >> 2) & 31);     // lanes of the partial iteration that hold data
+  uint32_t key[E];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < FI || pvalid) v = __ldg(reinterpret_cast<const float4 *>(cur.at((i * 32 + lane) * 4)));
+    key[4 * i + 0] = f2key_fast(v.x);
+    key[4 * i + 1] = f2key_fast(v.y);
+    key[4 * i + 2] = f2key_fast(v.z);
+    key[4 * i + 3] = f2key_fast(v.w);
+  }
+  // element e of lane l is row element ((e >> 2) * 32 + l) * 4 + (e & 3); slots of the partial iteration count only
+  // where pvalid
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+  for (int e = 0; e < FI * 4; ++e) {
+    kmin = min(kmin, key[e]);
+    kmax = max(kmax, key[e]);
+  }
+  if (PARTIAL && pvalid) {
+#pragma unroll
+    for (int e = FI * 4; e < E; ++e) {
+      kmin = min(kmin, key[e]);
+      kmax = max(kmax, key[e]);
+    }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  int shift = 32 - __clz((kmax - kmin) | 1u) - 8;            // ((kmax - kmin) >> shift) < 256
+  if (shift < 0) shift = 0;
+  uint32_t lo = kmin;                                        // candidates: keys in [lo, lo + span_m1]
+  uint32_t span_m1 = 0xffffffffu;
+  int need = k;
+  bool exact = false;
+  const uint32_t dummy = hist_addr + 256u * 4u;
+  // the scan shared by all passes: lane l owns bins 8 (31 - l) .. 8 (31 - l) + 7, walked from the top
+  auto scan = [&](int &bin, int &cntb) {
+    const int base = (31 - lane) * 8;
+    const uint4 hlo = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2];
+    const uint4 hhi = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2 + 1];
+    const int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
+    const int t = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    int incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
+    const int L = __ffs(hit) - 1;                            // candidates number >= need: a lane always hits
+    int packed = 0;                                          // bin | cntb << 8 | rem << 20
+    if (lane == L) {
+      int rem = need - (incl - t);
+      int bn = 0, cb = 0;
+      bool found = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (!found) {
+          if (c[i] >= rem) {
+            bn = base + 7 - i;
+            cb = c[i];
+            found = true;
+          } else {
+            rem -= c[i];
+          }
+        }
+      }
+      packed = bn | (cb << 8) | (rem << 20);                 // counts <= 2048 fit 12 bits
+    }
+    packed = __shfl_sync(0xffffffffu, packed, L);
+    bin = packed & 255;
+    cntb = (packed >> 8) & 4095;
+    need = packed >> 20;
+  };
+  // ---- pass 1: every key is a candidate ----
+  reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    uint32_t addr = hist_addr + (((key[e] - lo) >> shift) << 2);
+    if (e >= FI * 4) addr = pvalid ? addr : dummy;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+  }
+  __syncwarp();
+  int bin, cntb;
+  scan(bin, cntb);
+  lo += (uint32_t)bin << shift;                              // the boundary bucket is [lo, lo + (1 << shift))
+  if (cntb == need) {
+    exact = true;                                            // whole boundary bucket taken: every key >= lo wins
+  } else if (shift > 0) {
+    span_m1 = (1u << shift) - 1u;
+    if (cntb <= 32) {
+      // ---- the boundary bucket's keys, collected and ranked: T = its need-th largest ----
+      unsigned int *mine = s_cand[wib] + lane * TV_CSTRIDE;
+      uint32_t lp = (uint32_t)__cvta_generic_to_shared(mine);
+      const uint32_t lp0 = lp;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const bool in = ((key[e] - lo) <= span_m1) && (e < FI * 4 || pvalid);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "setp.ne.b32 q, %2, 0;\n\t"
+            "@q st.shared.u32 [%0], %1;\n\t"
+            "}\n" ::"r"(lp),
+            "r"(key[e]), "r"((uint32_t)in)
+            : "memory");
+        lp += in ? 4u : 0u;
+      }
+      const int mycnt = (int)((lp - lp0) >> 2);
+      int incl = mycnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      __syncwarp();
+      uint32_t mk[4];
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) mk[c2] = (c2 < mycnt) ? mine[c2] : 0u;
+      uint32_t more = __ballot_sync(0xffffffffu, mycnt > 4);
+      __syncwarp();
+      unsigned int *clist = s_cand[wib];                     // compact list (overwrites the lane lists: read first)
+      if (more == 0u) {
+        const int off = incl - mycnt;
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2)
+          if (c2 < mycnt) clist[off + c2] = mk[c2];
+        __syncwarp();
+        const uint32_t ci = (lane < cntb) ? clist[lane] : 0u;
+        int gt = 0, eqb = 0, eqt = 0;
+        for (int j = 0; j < cntb; ++j) {
+          const uint32_t cj = __shfl_sync(0xffffffffu, ci, j);
+          gt += (cj > ci) ? 1 : 0;
+          eqt += (cj == ci) ? 1 : 0;
+          eqb += (cj == ci && j < lane) ? 1 : 0;
+        }
+        // the candidate of rank need - 1 (ties broken by list position) carries the threshold
+        const uint32_t sel = __ballot_sync(0xffffffffu, lane < cntb && gt + eqb == need - 1);
+        const int src = __ffs(sel) - 1;
+        lo = __shfl_sync(0xffffffffu, ci, src);
+        const int gt_t = __shfl_sync(0xffffffffu, gt, src);
+        const int eq_t = __shfl_sync(0xffffffffu, eqt, src);
+        need -= gt_t;                                        // wanted among the keys == T
+        exact = (eq_t == need);
+        shift = 0;
+      } else {
+        exact = false;                                       // (a lane with > 4 candidates: histogram passes below)
+        cntb = 33;
+      }
+    }
+    if (!exact && cntb > 32) {
+      // ---- peaked row: further histogram passes over the bucket (up to 256 sub-buckets each) ----
+      shift = (shift > 8) ? shift - 8 : 0;
+#pragma unroll 1
+      for (;;) {
+        reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const uint32_t dk = key[e] - lo;
+          const bool in = (dk <= span_m1) && (e < FI * 4 || pvalid);
+          const uint32_t addr = in ? hist_addr + ((dk >> shift) << 2) : dummy;
+          asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+        }
+        __syncwarp();
+        scan(bin, cntb);
+        lo += (uint32_t)bin << shift;
+        if (cntb == need) {
+          exact = true;
+          break;
+        }
+        if (shift == 0) break;                               // bucket == one key value: `need` of its duplicates win
+        span_m1 = (1u << shift) - 1u;
+        shift = (shift > 8) ? shift - 8 : 0;
+      }
+    }
+  }
+  const uint32_t T = lo;
+  __syncwarp();
+  {
+    uint4 *b4 = reinterpret_cast<uint4 *>(hist);
+    b4[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+    b4[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncwarp();
+  const uint32_t lane4 = (uint32_t)lane << 2;
+  if (exact) {
+    // ---- lane-local compaction: every key >= T wins ----
+    int cnt = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) cnt += (key[e] >= T && (e < FI * 4 || pvalid)) ? 1 : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t pos = hist_addr + 8u * (uint32_t)(incl - cnt);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool win = key[e] >= T && (e < FI * 4 || pvalid);
+      const uint32_t id = lane4 + (uint32_t)((e >> 2) * 128 + (e & 3));
+      st_shared_v2_if(pos, ~id, key[e], win);
+      pos += win ? 8u : 0u;
+    }
+  } else {
+    // ---- boundary ties: every key > T wins, and the `need` lowest-index elements with key == T ----
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int basec = 0, need_eq = need;
+#pragma unroll 1
+    for (int i = 0; i < NI; ++i) {
+      const bool ok = (i < FI) || pvalid;
+      uint32_t m_eq[4], m_gt[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t kv = 0u;
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii)
+          if (ii == i) kv = key[4 * ii + cc];
+        m_eq[cc] = __ballot_sync(0xffffffffu, ok && kv == T);
+        m_gt[cc] = __ballot_sync(0xffffffffu, ok && kv > T);
+      }
+      // index order inside the iteration: lane major, then component
+      const int eq_before_lane = __popc(m_eq[0] & lt_mask) + __popc(m_eq[1] & lt_mask) + __popc(m_eq[2] & lt_mask) +
+                                 __popc(m_eq[3] & lt_mask);
+      const int eq_total = __popc(m_eq[0]) + __popc(m_eq[1]) + __popc(m_eq[2]) + __popc(m_eq[3]);
+      int my_eq = 0, my_win[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const bool eq = (m_eq[cc] >> lane) & 1u, gt = (m_gt[cc] >> lane) & 1u;
+        my_win[cc] = (gt || (eq && eq_before_lane + my_eq < need_eq)) ? 1 : 0;
+        my_eq += eq ? 1 : 0;
+      }
+      const int my_cnt = my_win[0] + my_win[1] + my_win[2] + my_win[3];
+      int incl = my_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int slot = basec + incl - my_cnt;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t kv = 0u;
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii)
+          if (ii == i) kv = key[4 * ii + cc];
+        if (my_win[cc]) buf[slot++] = make_uint2(~(lane4 + (uint32_t)(i * 128 + cc)), kv);
+      }
+      basec += __shfl_sync(0xffffffffu, incl, 31);
+      need_eq -= min(need_eq, eq_total);
+    }
+  }
+  __syncwarp();
+  float *vrow = vals + (size_t)r * k;
+  int *irow = idx + (size_t)r * k;
+  if (SORTED) {
+    unsigned long long c4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c4[i] = reinterpret_cast<const unsigned long long *>(hist)[lane * 4 + i];
+    bitonic_step_reg<2, 1>(c4, lane);
+    bitonic_step_reg<4, 2>(c4, lane);   bitonic_step_reg<4, 1>(c4, lane);
+    bitonic_step_reg<8, 4>(c4, lane);   bitonic_step_reg<8, 2>(c4, lane);   bitonic_step_reg<8, 1>(c4, lane);
+    bitonic_step_reg<16, 8>(c4, lane);  bitonic_step_reg<16, 4>(c4, lane);  bitonic_step_reg<16, 2>(c4, lane);
+    bitonic_step_reg<16, 1>(c4, lane);
+    bitonic_step_reg<32, 16>(c4, lane); bitonic_step_reg<32, 8>(c4, lane);  bitonic_step_reg<32, 4>(c4, lane);
+    bitonic_step_reg<32, 2>(c4, lane);  bitonic_step_reg<32, 1>(c4, lane);
+    bitonic_step_reg<64, 32>(c4, lane); bitonic_step_reg<64, 16>(c4, lane); bitonic_step_reg<64, 8>(c4, lane);
+    bitonic_step_reg<64, 4>(c4, lane);  bitonic_step_reg<64, 2>(c4, lane);  bitonic_step_reg<64, 1>(c4, lane);
+    bitonic_step_reg<128, 64>(c4, lane); bitonic_step_reg<128, 32>(c4, lane); bitonic_step_reg<128, 16>(c4, lane);
+    bitonic_step_reg<128, 8>(c4, lane);  bitonic_step_reg<128, 4>(c4, lane);  bitonic_step_reg<128, 2>(c4, lane);
+    bitonic_step_reg<128, 1>(c4, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p2 = lane * 4 + i;
+      if (p2 < k) {
+        vrow[p2] = key2f((uint32_t)(c4[i] >> 32));
+        irow[p2] = (int)~(uint32_t)(c4[i] & 0xffffffffu);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t2 = lane + 32 * i;
+      if (t2 < k) {
+        const uint2 cc = buf[t2];
+        vrow[t2] = key2f(cc.y);
+        irow[t2] = (int)~cc.x;
+      }
+    }
+  }
+}
+
 // One 256-thread block per row, any width: three radix passes (11 + 11 + 10 bits) with shared-memory
 // histograms; pass 1 streams the row from global memory, the candidates of the winning bucket are
 // compacted to shared memory for the later passes (falls back to re-streaming if they do not fit).
@@ -970,6 +1301,26 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   const int KP = next_pow2(k < 32 ? 32 : k);
   EDRL_CHECK_ARG(KP <= 1024, "topk: k = %d is larger than the supported 1024", k);
   static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
+  static const bool novec = (getenv("EDRL_TOPK_VEC") != nullptr && atoi(getenv("EDRL_TOPK_VEC")) == 0);
+  if (uniform && Wmax <= 2048 && k <= 128 && !legacy && !novec && rows.vec4_ok()) {
+    // vectorised warp select for the common uniform widths (W / 4 = 32 FI + partial lanes)
+    const int W4 = Wmax >> 2, fi = W4 >> 5;
+    const bool part = (W4 & 31) != 0;
+    const int grid = (R + 3) / 4;
+    bool done = true;
+#define EDRL_VEC_CASE(FI_, P_)                                                                                   \
+  if (fi == FI_ && part == P_) {                                                                                 \
+    if (sorted) topk_vec_kernel<FI_, P_, true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, vals, idx);        \
+    else topk_vec_kernel<FI_, P_, false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, vals, idx);              \
+  } else
+    EDRL_VEC_CASE(0, true) EDRL_VEC_CASE(1, true) EDRL_VEC_CASE(2, false) EDRL_VEC_CASE(4, false)
+    EDRL_VEC_CASE(6, true) EDRL_VEC_CASE(8, false) EDRL_VEC_CASE(12, true) EDRL_VEC_CASE(16, false) { done = false; }
+#undef EDRL_VEC_CASE
+    if (done) {
+      EDRL_LAUNCHED();
+      return 0;
+    }
+  }
   if (Wmax <= 2048 && k <= 128 && !legacy) {
     const bool full = uniform && (Wmax % 32 == 0);
     if (Wmax <= 256) launch_radix<8>(rows, R, k, sorted, full && Wmax == 256, vals, idx, st);
