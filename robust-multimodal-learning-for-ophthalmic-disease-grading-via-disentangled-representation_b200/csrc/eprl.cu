@@ -401,7 +401,7 @@ score_bwd_dzpn_kernel(const float *__restrict__ datt, const float *__restrict__ 
 // ----------------------------------------------------------------------------- K7 top-k
 // Order-preserving key: larger float <=> larger uint32 (positive NaN sorts first, like torch.topk).
 __device__ __forceinline__ uint32_t f2key(float x) {
-  const uint32_t u = __float_as_uint(x);
+  const uint32_t u = __float_as_uint(x + 0.f);               // -0 -> +0: the two compare equal, so they must tie
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 __device__ __forceinline__ float key2f(uint32_t k) {
@@ -609,7 +609,7 @@ __device__ __forceinline__ void bitonic_step_reg(unsigned long long (&c)[4], int
 
 // order-preserving key with two integer ops: flip all bits of negatives, only the sign bit of the rest
 __device__ __forceinline__ uint32_t f2key_fast(float x) {
-  const uint32_t u = __float_as_uint(x);
+  const uint32_t u = __float_as_uint(x + 0.f);               // -0 -> +0: the two compare equal, so they must tie
   return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
 }
 // hist[dg] += 1 if (key >= lo && dg < nbins), as ONE predicated shared-memory reduction (no branch)
@@ -639,14 +639,12 @@ __device__ __forceinline__ void st_shared_v2_if(uint32_t addr, uint32_t x, uint3
 }
 
 // FULL: W == 32 E exactly (no bounds checks, no padding keys).
+// One row by one warp; `hist` = 256 words of warp-private shared memory.  INLINE = false: the rare-path fallback of
+// topk_vec_kernel (re-reads the row from global memory, kept out of line so that it does not cost the fast path
+// registers).
 template <int E, bool FULL, bool SORTED, class Rows>
-__global__ void __launch_bounds__(128)
-topk_warp_radix_kernel(Rows rows, int R, int k, float *__restrict__ vals, int *__restrict__ idx) {
-  __shared__ __align__(16) unsigned int s_hist[4][256];      // per warp: histogram, later 128 64-bit winners
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 4 + wib;
-  if (r >= R) return;
-  unsigned int *hist = s_hist[wib];
+__device__ __forceinline__ void radix_select_row(const Rows &rows, int r, int k, unsigned int *hist, int lane,
+                                                 float *__restrict__ vals, int *__restrict__ idx) {
   uint2 *buf = reinterpret_cast<uint2 *>(hist);              // .x = ~index, .y = key  (little-endian key|~index)
   const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(hist);
   const int W = FULL ? E * 32 : rows.width(r);
@@ -797,24 +795,41 @@ topk_warp_radix_kernel(Rows rows, int R, int k, float *__restrict__ vals, int *_
   }
 }
 
+template <int E, bool FULL, bool SORTED, class Rows>
+__global__ void __launch_bounds__(128)
+topk_warp_radix_kernel(Rows rows, int R, int k, float *__restrict__ vals, int *__restrict__ idx) {
+  __shared__ __align__(16) unsigned int s_hist[4][256];      // per warp: histogram, later 128 64-bit winners
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 4 + wib;
+  if (r >= R) return;
+  radix_select_row<E, FULL, SORTED, Rows>(rows, r, k, s_hist[wib], lane, vals, idx);
+}
+template <int E, bool SORTED, class Rows>
+__device__ __noinline__ void radix_select_row_slow(const Rows &rows, int r, int k, unsigned int *hist, int lane,
+                                                   float *__restrict__ vals, int *__restrict__ idx) {
+  radix_select_row<E, false, SORTED, Rows>(rows, r, k, hist, lane, vals, idx);
+}
+
 // ----------------------------------------------------------------------------- K7b vectorised warp select
-// One warp per row, uniform row width W (a multiple of 4, rows 16-byte aligned), k <= 128.  Same range-adaptive MSD
-// radix select as topk_warp_radix_kernel, rebuilt around the instruction count (the select is bound by instruction
-// issue / the integer pipe, not by HBM):
+// One warp per row, uniform row width W (a multiple of 4, rows 16-byte aligned), k <= 128.  The select is bound by
+// instruction issue and the integer pipe, not by HBM, so it is built around the instruction count:
 //   * 128-bit loads: lane l holds float4 number i * 32 + l of the row for i < FI (+ one partial iteration);
-//   * the first histogram pass is unpredicated (every key lies in [kmin, kmax]; lanes without data in the partial
-//     iteration count into a dummy bin), 4 instructions per element;
-//   * the boundary bucket of that pass normally holds a handful of keys: they are collected (lane-local lists, one
-//     warp prefix) and ranked against each other with shuffles, instead of a second and third histogram pass over the
-//     whole row; more than 32 candidates (peaked rows) fall back to further histogram passes;
-//   * winners are compacted LANE-LOCALLY (count, one warp prefix over the 32 lane totals, predicated stores) instead of
-//     one ballot + two popcounts per element -- the unsorted output order is by lane, which edrl_topk_rows(sorted = 0)
-//     leaves unspecified; boundary ties (fewer wanted than present at the threshold key) take a ballot path that
-//     keeps the lowest indices;
-//   * SORTED: the winners (key | ~index composites in shared memory) go through the register bitonic network.
+//   * ONE histogram pass over 256 bins that are uniform in VALUE between the row's min and max: bin = the low bits of
+//     fma(x - min, scale, 2^23), i.e. FADD + FFMA (fma pipe) + mask + address + red per element.  (Bins uniform in the
+//     order-preserving integer key are one binade wide around 1.0: 110 of N(0,1)'s 800 values share the threshold's bin
+//     and two more passes are needed; value bins leave 4 or 5.)
+//   * the threshold bin's values are collected (lane-local lists, one warp prefix) and ranked against each other with
+//     shuffles: T = the need-th largest of them;
+//   * winners (x >= T) are compacted lane-locally (count, one warp prefix, predicated stores) instead of one ballot and
+//     two popcounts per element -- the unsorted output order is by lane, which edrl_topk_rows(sorted = 0) leaves
+//     unspecified; ties at T (fewer wanted than present) take a ballot path that keeps the lowest indices;
+//   * SORTED: the winners go through the register bitonic network as key | ~index composites.
+// Rows holding NaN or infinities, constant rows, a threshold bin with more than 32 values or a lane with more than 4
+// of them take radix_select_row (the integer-key select above) instead.  Comparisons are on float values: -0 and +0
+// tie (lowest index first), as in torch.topk.
 // FI: full iterations (W / 128), PARTIAL: one more with lanes < (W / 4) % 32.
-constexpr int TV_HIST = 260;                  // 256 bins + dummy bin (16-byte aligned rows)
-constexpr int TV_CSTRIDE = 33;                // words per lane of the candidate staging area (at most 32 candidates; odd: conflict free)
+constexpr int TV_HIST = 264;                  // 256 bins + overflow / dummy bins (16-byte aligned rows)
+constexpr int TV_CSTRIDE = 5;                 // words per lane of the candidate staging area (4 candidates + 1: odd)
 template <int FI, bool PARTIAL, bool SORTED, class Rows>
 __global__ void __launch_bounds__(128)
 topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
@@ -826,50 +841,78 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
   const int r = blockIdx.x * 4 + wib;
   if (r >= R) return;
   unsigned int *hist = s_hist[wib];
-  uint2 *buf = reinterpret_cast<uint2 *>(hist);              // .x = ~index, .y = key  (little-endian key|~index)
+  uint2 *buf = reinterpret_cast<uint2 *>(hist);              // .x = ~index, .y = value bits
   const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(hist);
   const typename Rows::Cursor cur = rows.cursor(r);
   const bool pvalid = PARTIAL && lane < ((W >> 2) & 31);     // lanes of the partial iteration that hold data
-  uint32_t key[E];
+  // element e of lane l is row element ((e >> 2) * 32 + l) * 4 + (e & 3); slots of the partial iteration count only
+  // where pvalid
+  float x[E];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < FI || pvalid) v = __ldg(reinterpret_cast<const float4 *>(cur.at((i * 32 + lane) * 4)));
-    key[4 * i + 0] = f2key_fast(v.x);
-    key[4 * i + 1] = f2key_fast(v.y);
-    key[4 * i + 2] = f2key_fast(v.z);
-    key[4 * i + 3] = f2key_fast(v.w);
+    x[4 * i + 0] = v.x;
+    x[4 * i + 1] = v.y;
+    x[4 * i + 2] = v.z;
+    x[4 * i + 3] = v.w;
   }
-  // element e of lane l is row element ((e >> 2) * 32 + l) * 4 + (e & 3); slots of the partial iteration count only
-  // where pvalid
-  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  // min, max and a NaN / infinity detector (x * 0 is NaN for either)
+  float xmin = x[0], xmax = x[0], nf = 0.f;
+  if (FI == 0) {
+    xmin = pvalid ? x[0] : __int_as_float(0x7f800000);
+    xmax = pvalid ? x[0] : __int_as_float(0xff800000);
+  }
 #pragma unroll
   for (int e = 0; e < FI * 4; ++e) {
-    kmin = min(kmin, key[e]);
-    kmax = max(kmax, key[e]);
+    xmin = fminf(xmin, x[e]);
+    xmax = fmaxf(xmax, x[e]);
+    nf = fmaf(x[e], 0.f, nf);
   }
   if (PARTIAL && pvalid) {
 #pragma unroll
     for (int e = FI * 4; e < E; ++e) {
-      kmin = min(kmin, key[e]);
-      kmax = max(kmax, key[e]);
+      xmin = fminf(xmin, x[e]);
+      xmax = fmaxf(xmax, x[e]);
+      nf = fmaf(x[e], 0.f, nf);
     }
   }
-  kmin = __reduce_min_sync(0xffffffffu, kmin);
-  kmax = __reduce_max_sync(0xffffffffu, kmax);
-  int shift = 32 - __clz((kmax - kmin) | 1u) - 8;            // ((kmax - kmin) >> shift) < 256
-  if (shift < 0) shift = 0;
-  uint32_t lo = kmin;                                        // candidates: keys in [lo, lo + span_m1]
-  uint32_t span_m1 = 0xffffffffu;
+  {
+    const uint32_t kmin = __reduce_min_sync(0xffffffffu, f2key_fast(xmin));
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, f2key_fast(xmax));
+    xmin = key2f(kmin);
+    xmax = key2f(kmax);
+  }
+  const float range = xmax - xmin;
+  const bool irregular = __any_sync(0xffffffffu, !(nf == 0.f)) || !(range > 0.f) || !(range <= 3.0e38f);
+  bool done = false, exact = false;
   int need = k;
-  bool exact = false;
-  const uint32_t dummy = hist_addr + 256u * 4u;
-  // the scan shared by all passes: lane l owns bins 8 (31 - l) .. 8 (31 - l) + 7, walked from the top
-  auto scan = [&](int &bin, int &cntb) {
+  float T = 0.f;
+  if (!irregular) {
+    // ---- one histogram pass over value bins: bin(x) = round((x - xmin) * 255 / range) in [0, 255] ----
+    // y = (x - xmin) scale + 2^23 in [2^23, 2^23 + 255.5): bin = y's low bits.  (x - xmin >= 0 exactly; folding xmin into
+    // the addend would round it to an integer and push the smallest values below 2^23.)
+    const float scale = 255.f / range;
+    const float off = 8388608.f;
+    reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < 2) reinterpret_cast<uint4 *>(hist)[64 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    const uint32_t dummy = hist_addr + 260u * 4u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t yb = __float_as_uint(fmaf(x[e] - xmin, scale, off));
+      uint32_t addr = hist_addr + ((yb & 0x1ffu) << 2);      // (rounding may reach bin 256: counted, scanned as bin 255)
+      if (e >= FI * 4) addr = pvalid ? addr : dummy;
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    }
+    __syncwarp();
+    // lane l owns bins 8 (31 - l) .. 8 (31 - l) + 7, walked from the top: lane 0 holds the 8 largest
     const int base = (31 - lane) * 8;
     const uint4 hlo = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2];
     const uint4 hhi = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2 + 1];
-    const int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
+    int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
+    const int over = (int)hist[256];                         // bin 256 (fp rounding at the very top): above bin 255
     const int t = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
     int incl = t;
 #pragma unroll
@@ -877,9 +920,10 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
+    incl += over;
     const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
-    const int L = __ffs(hit) - 1;                            // candidates number >= need: a lane always hits
-    int packed = 0;                                          // bin | cntb << 8 | rem << 20
+    const int L = __ffs(hit) - 1;
+    int packed = 0;                                          // bin | cntb << 9 | rem << 21
     if (lane == L) {
       int rem = need - (incl - t);
       int bn = 0, cb = 0;
@@ -896,120 +940,67 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
           }
         }
       }
-      packed = bn | (cb << 8) | (rem << 20);                 // counts <= 2048 fit 12 bits
+      packed = bn | (cb << 9) | (rem << 21);
     }
-    packed = __shfl_sync(0xffffffffu, packed, L);
-    bin = packed & 255;
-    cntb = (packed >> 8) & 4095;
-    need = packed >> 20;
-  };
-  // ---- pass 1: every key is a candidate ----
-  reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
-  reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
-  __syncwarp();
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    uint32_t addr = hist_addr + (((key[e] - lo) >> shift) << 2);
-    if (e >= FI * 4) addr = pvalid ? addr : dummy;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-  }
-  __syncwarp();
-  int bin, cntb;
-  scan(bin, cntb);
-  lo += (uint32_t)bin << shift;                              // the boundary bucket is [lo, lo + (1 << shift))
-  if (cntb == need) {
-    exact = true;                                            // whole boundary bucket taken: every key >= lo wins
-  } else if (shift > 0) {
-    span_m1 = (1u << shift) - 1u;
-    if (cntb <= 32) {
-      // ---- the boundary bucket's keys, collected and ranked: T = its need-th largest ----
+    // (need <= over cannot happen for k <= W unless bin 256 alone holds k values: then rem <= 0 and cb = 0 below)
+    packed = __shfl_sync(0xffffffffu, packed, L < 0 ? 0 : L);
+    const int bin = packed & 511, cntb = (packed >> 9) & 4095;
+    const int rem = packed >> 21;
+    if (L >= 0 && rem >= 1 && cntb >= rem && cntb <= 32) {
+      // ---- the threshold bin's values, collected and ranked: T = its rem-th largest ----
+      const uint32_t ytarget = 0x4b000000u + (uint32_t)bin;
       unsigned int *mine = s_cand[wib] + lane * TV_CSTRIDE;
-      uint32_t lp = (uint32_t)__cvta_generic_to_shared(mine);
-      const uint32_t lp0 = lp;
+      int mycnt = 0;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const bool in = ((key[e] - lo) <= span_m1) && (e < FI * 4 || pvalid);
-        asm volatile(
-            "{\n\t"
-            ".reg .pred q;\n\t"
-            "setp.ne.b32 q, %2, 0;\n\t"
-            "@q st.shared.u32 [%0], %1;\n\t"
-            "}\n" ::"r"(lp),
-            "r"(key[e]), "r"((uint32_t)in)
-            : "memory");
-        lp += in ? 4u : 0u;
+        const bool in = (__float_as_uint(fmaf(x[e] - xmin, scale, off)) == ytarget) && (e < FI * 4 || pvalid);
+        if (in && mycnt < 4) mine[mycnt] = __float_as_uint(x[e]);
+        mycnt += in ? 1 : 0;
       }
-      const int mycnt = (int)((lp - lp0) >> 2);
-      int incl = mycnt;
+      int cincl = mycnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        const int v = __shfl_up_sync(0xffffffffu, cincl, o);
+        if (lane >= o) cincl += v;
       }
-      __syncwarp();
-      uint32_t mk[4];
-#pragma unroll
-      for (int c2 = 0; c2 < 4; ++c2) mk[c2] = (c2 < mycnt) ? mine[c2] : 0u;
-      uint32_t more = __ballot_sync(0xffffffffu, mycnt > 4);
-      __syncwarp();
-      unsigned int *clist = s_cand[wib];                     // compact list (overwrites the lane lists: read first)
+      const uint32_t more = __ballot_sync(0xffffffffu, mycnt > 4);
       if (more == 0u) {
-        const int off = incl - mycnt;
+        __syncwarp();
+        uint32_t mk[4];
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) mk[c2] = (c2 < mycnt) ? mine[c2] : 0u;
+        __syncwarp();
+        unsigned int *clist = s_cand[wib];                   // compact list (overwrites the lane lists: read first)
+        const int coff = cincl - mycnt;
 #pragma unroll
         for (int c2 = 0; c2 < 4; ++c2)
-          if (c2 < mycnt) clist[off + c2] = mk[c2];
+          if (c2 < mycnt) clist[coff + c2] = mk[c2];
         __syncwarp();
-        const uint32_t ci = (lane < cntb) ? clist[lane] : 0u;
+        const float ci = (lane < cntb) ? __uint_as_float(clist[lane]) : 0.f;
         int gt = 0, eqb = 0, eqt = 0;
         for (int j = 0; j < cntb; ++j) {
-          const uint32_t cj = __shfl_sync(0xffffffffu, ci, j);
+          const float cj = __shfl_sync(0xffffffffu, ci, j);
           gt += (cj > ci) ? 1 : 0;
           eqt += (cj == ci) ? 1 : 0;
           eqb += (cj == ci && j < lane) ? 1 : 0;
         }
-        // the candidate of rank need - 1 (ties broken by list position) carries the threshold
-        const uint32_t sel = __ballot_sync(0xffffffffu, lane < cntb && gt + eqb == need - 1);
+        // the candidate of rank rem - 1 (ties broken by list position) carries the threshold
+        const uint32_t sel = __ballot_sync(0xffffffffu, lane < cntb && gt + eqb == rem - 1);
         const int src = __ffs(sel) - 1;
-        lo = __shfl_sync(0xffffffffu, ci, src);
+        T = __shfl_sync(0xffffffffu, ci, src);
         const int gt_t = __shfl_sync(0xffffffffu, gt, src);
         const int eq_t = __shfl_sync(0xffffffffu, eqt, src);
-        need -= gt_t;                                        // wanted among the keys == T
+        need = rem - gt_t;                                   // wanted among the values == T
         exact = (eq_t == need);
-        shift = 0;
-      } else {
-        exact = false;                                       // (a lane with > 4 candidates: histogram passes below)
-        cntb = 33;
-      }
-    }
-    if (!exact && cntb > 32) {
-      // ---- peaked row: further histogram passes over the bucket (up to 256 sub-buckets each) ----
-      shift = (shift > 8) ? shift - 8 : 0;
-#pragma unroll 1
-      for (;;) {
-        reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
-        reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-          const uint32_t dk = key[e] - lo;
-          const bool in = (dk <= span_m1) && (e < FI * 4 || pvalid);
-          const uint32_t addr = in ? hist_addr + ((dk >> shift) << 2) : dummy;
-          asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-        }
-        __syncwarp();
-        scan(bin, cntb);
-        lo += (uint32_t)bin << shift;
-        if (cntb == need) {
-          exact = true;
-          break;
-        }
-        if (shift == 0) break;                               // bucket == one key value: `need` of its duplicates win
-        span_m1 = (1u << shift) - 1u;
-        shift = (shift > 8) ? shift - 8 : 0;
+        done = true;
       }
     }
   }
-  const uint32_t T = lo;
+  if (!done) {
+    // NaN / infinity, constant row, or a crowded threshold bin: the integer-key radix select, from global memory
+    radix_select_row_slow<E, SORTED, Rows>(rows, r, k, hist, lane, vals, idx);
+    return;
+  }
   __syncwarp();
   {
     uint4 *b4 = reinterpret_cast<uint4 *>(hist);
@@ -1019,10 +1010,10 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
   __syncwarp();
   const uint32_t lane4 = (uint32_t)lane << 2;
   if (exact) {
-    // ---- lane-local compaction: every key >= T wins ----
+    // ---- lane-local compaction: every x >= T wins ----
     int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) cnt += (key[e] >= T && (e < FI * 4 || pvalid)) ? 1 : 0;
+    for (int e = 0; e < E; ++e) cnt += (x[e] >= T && (e < FI * 4 || pvalid)) ? 1 : 0;
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1032,13 +1023,13 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     uint32_t pos = hist_addr + 8u * (uint32_t)(incl - cnt);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const bool win = key[e] >= T && (e < FI * 4 || pvalid);
+      const bool win = x[e] >= T && (e < FI * 4 || pvalid);
       const uint32_t id = lane4 + (uint32_t)((e >> 2) * 128 + (e & 3));
-      st_shared_v2_if(pos, ~id, key[e], win);
+      st_shared_v2_if(pos, ~id, __float_as_uint(x[e]), win);
       pos += win ? 8u : 0u;
     }
   } else {
-    // ---- boundary ties: every key > T wins, and the `need` lowest-index elements with key == T ----
+    // ---- ties at T: every x > T wins, and the `need` lowest-index elements with x == T ----
     const uint32_t lt_mask = (1u << lane) - 1u;
     int basec = 0, need_eq = need;
 #pragma unroll 1
@@ -1047,12 +1038,12 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       uint32_t m_eq[4], m_gt[4];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t kv = 0u;
+        float xv = 0.f;
 #pragma unroll
         for (int ii = 0; ii < NI; ++ii)
-          if (ii == i) kv = key[4 * ii + cc];
-        m_eq[cc] = __ballot_sync(0xffffffffu, ok && kv == T);
-        m_gt[cc] = __ballot_sync(0xffffffffu, ok && kv > T);
+          if (ii == i) xv = x[4 * ii + cc];
+        m_eq[cc] = __ballot_sync(0xffffffffu, ok && xv == T);
+        m_gt[cc] = __ballot_sync(0xffffffffu, ok && xv > T);
       }
       // index order inside the iteration: lane major, then component
       const int eq_before_lane = __popc(m_eq[0] & lt_mask) + __popc(m_eq[1] & lt_mask) + __popc(m_eq[2] & lt_mask) +
@@ -1075,11 +1066,11 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       int slot = basec + incl - my_cnt;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t kv = 0u;
+        float xv = 0.f;
 #pragma unroll
         for (int ii = 0; ii < NI; ++ii)
-          if (ii == i) kv = key[4 * ii + cc];
-        if (my_win[cc]) buf[slot++] = make_uint2(~(lane4 + (uint32_t)(i * 128 + cc)), kv);
+          if (ii == i) xv = x[4 * ii + cc];
+        if (my_win[cc]) buf[slot++] = make_uint2(~(lane4 + (uint32_t)(i * 128 + cc)), __float_as_uint(xv));
       }
       basec += __shfl_sync(0xffffffffu, incl, 31);
       need_eq -= min(need_eq, eq_total);
@@ -1089,9 +1080,15 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
   float *vrow = vals + (size_t)r * k;
   int *irow = idx + (size_t)r * k;
   if (SORTED) {
+    // composites key | ~index (value bits -> order-preserving key; empty slots stay 0 = below every key; -0 and +0
+    // get the same key so that they order by index)
     unsigned long long c4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) c4[i] = reinterpret_cast<const unsigned long long *>(hist)[lane * 4 + i];
+    for (int i = 0; i < 4; ++i) {
+      const uint2 w = buf[lane * 4 + i];
+      const uint32_t kk = (lane * 4 + i < k) ? f2key_fast(__uint_as_float(w.y)) : 0u;
+      c4[i] = ((unsigned long long)kk << 32) | w.x;
+    }
     bitonic_step_reg<2, 1>(c4, lane);
     bitonic_step_reg<4, 2>(c4, lane);   bitonic_step_reg<4, 1>(c4, lane);
     bitonic_step_reg<8, 4>(c4, lane);   bitonic_step_reg<8, 2>(c4, lane);   bitonic_step_reg<8, 1>(c4, lane);
@@ -1108,8 +1105,9 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     for (int i = 0; i < 4; ++i) {
       const int p2 = lane * 4 + i;
       if (p2 < k) {
+        const int id = (int)~(uint32_t)(c4[i] & 0xffffffffu);
         vrow[p2] = key2f((uint32_t)(c4[i] >> 32));
-        irow[p2] = (int)~(uint32_t)(c4[i] & 0xffffffffu);
+        irow[p2] = id;
       }
     }
   } else {
@@ -1118,7 +1116,7 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       const int t2 = lane + 32 * i;
       if (t2 < k) {
         const uint2 cc = buf[t2];
-        vrow[t2] = key2f(cc.y);
+        vrow[t2] = __uint_as_float(cc.y);
         irow[t2] = (int)~cc.x;
       }
     }

@@ -79,6 +79,49 @@ def test_topk_ties_and_specials(W):
         edrl_b200.topk_rows(big, W + 38)
 
 
+@pytest.mark.parametrize("W,k", [(800, 100), (1600, 100), (1024, 128), (2048, 100), (216, 32), (144, 144 // 2), (100, 7),
+                                 (512, 1), (256, 100)])
+def test_topk_vectorised_select_paths(W, k):
+    """The vectorised warp select (csrc/eprl.cu topk_vec_kernel) and every way out of its fast path: ties at the
+    threshold, +-0, a crowded threshold bin (> 32 values, or > 4 in one lane), constant rows, NaN / infinities."""
+    import edrl_b200
+    rng = np.random.default_rng(W * 31 + k)
+    rows = []
+    rows.append(rng.standard_normal(W))                                           # plain
+    r = rng.standard_normal(W); r[rng.integers(0, W, W // 3)] = 0.0; r[rng.integers(0, W, W // 3)] = -0.0
+    rows.append(r)                                                                # many +-0 (ties around 0)
+    r = rng.standard_normal(W) * 1e-3; r[:W // 2] = np.round(r[:W // 2], 4)
+    rows.append(r)                                                                # duplicates from rounding
+    r = np.full(W, 2.5); r[::7] = 3.0; r[1::7] = -1.0
+    rows.append(r)                                                                # three values only
+    r = rng.standard_normal(W); r[5] = 1e30; r[6] = -1e30
+    rows.append(r)                                                                # outliers squeeze everything into 2 bins
+    r = rng.standard_normal(W); r[W // 2] = np.nan
+    rows.append(r)                                                                # NaN first, like torch.topk
+    r = rng.standard_normal(W); r[3] = np.inf; r[W - 1] = -np.inf
+    rows.append(r)
+    rows.append(np.full(W, -7.0))                                                 # constant
+    r = rng.standard_normal(W); r[: 4 * 8] = r[0]
+    rows.append(r)                                                                # one lane's float4s all equal
+    rows.append(np.arange(W, dtype=np.float64))                                   # ascending
+    rows.append(-np.arange(W, dtype=np.float64))                                  # descending
+    rows.append(rng.standard_normal(W) * 1e-30)                                   # tiny range
+    x = np.stack(rows).astype(np.float32)
+    for srt in (True, False):
+        v, i = edrl_b200.topk_rows(dev(x), k, sorted=srt)
+        v, i = v.cpu().numpy(), i.cpu().numpy()
+        for rr in range(x.shape[0]):
+            xr = x[rr]
+            keyed = np.where(np.isnan(xr), np.inf, xr).astype(np.float64)
+            order = np.lexsort((np.arange(W), -keyed, ~np.isnan(xr)))[:k]        # NaN first, then value desc, index asc
+            if srt:
+                np.testing.assert_array_equal(i[rr], order.astype(np.int32), err_msg=f"row {rr}")
+                np.testing.assert_array_equal(v[rr], xr[order], err_msg=f"row {rr}")
+            else:
+                np.testing.assert_array_equal(np.sort(i[rr]), np.sort(order).astype(np.int32), err_msg=f"row {rr}")
+                np.testing.assert_array_equal(v[rr], xr[i[rr]], err_msg=f"row {rr}")
+
+
 # ---------------------------------------------------------------- label-addressed select + loss
 @pytest.mark.parametrize("B,C,S,k", [(4, 2, 800, 100), (64, 2, 800, 100), (5, 3, 300, 100), (2, 4, 1000, 100)])
 def test_select_topk_matches_split_plus_topk(B, C, S, k):
