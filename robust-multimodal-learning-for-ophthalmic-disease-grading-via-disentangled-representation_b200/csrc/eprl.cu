@@ -829,9 +829,9 @@ __device__ __noinline__ void radix_select_row_slow(const Rows &rows, int r, int 
 // tie (lowest index first), as in torch.topk.
 // FI: full iterations (W / 128), PARTIAL: one more with lanes < (W / 4) % 32.
 constexpr int TV_HIST = 264;                  // 256 bins + overflow / dummy bins (16-byte aligned rows)
-constexpr int TV_CSTRIDE = 5;                 // words per lane of the candidate staging area (4 candidates + 1: odd)
+constexpr int TV_CSTRIDE = 33;                // words per lane of the candidate staging area (a bin taken here holds <= 32; odd)
 template <int FI, bool PARTIAL, bool SORTED, class Rows>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (FI <= 6 && !SORTED) ? 8 : 4)
 topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
   constexpr int NI = FI + (PARTIAL ? 1 : 0);
   constexpr int E = NI * 4;
@@ -950,13 +950,23 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       // ---- the threshold bin's values, collected and ranked: T = its rem-th largest ----
       const uint32_t ytarget = 0x4b000000u + (uint32_t)bin;
       unsigned int *mine = s_cand[wib] + lane * TV_CSTRIDE;
-      int mycnt = 0;
+      uint32_t lp = (uint32_t)__cvta_generic_to_shared(mine);
+      const uint32_t lp0 = lp;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const bool in = (__float_as_uint(fmaf(x[e] - xmin, scale, off)) == ytarget) && (e < FI * 4 || pvalid);
-        if (in && mycnt < 4) mine[mycnt] = __float_as_uint(x[e]);
-        mycnt += in ? 1 : 0;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "setp.ne.b32 q, %2, 0;\n\t"
+            "@q st.shared.b32 [%0], %1;\n\t"
+            "@q add.u32 %0, %0, 4;\n\t"
+            "}\n"
+            : "+r"(lp)
+            : "r"(__float_as_uint(x[e])), "r"((uint32_t)in)
+            : "memory");
       }
+      const int mycnt = (int)((lp - lp0) >> 2);
       int cincl = mycnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -1011,9 +1021,25 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
   const uint32_t lane4 = (uint32_t)lane << 2;
   if (exact) {
     // ---- lane-local compaction: every x >= T wins ----
+    // (the win flags are kept in an explicit bit mask: the compiler otherwise rebuilds one with three instructions
+    //  per element to share the compares between the counting and the storing sweep)
+    uint32_t wm[(E + 31) / 32];
+#pragma unroll
+    for (int w2 = 0; w2 < (E + 31) / 32; ++w2) wm[w2] = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const bool win = x[e] >= T && (e < FI * 4 || pvalid);
+      asm("{\n\t"
+          ".reg .pred q;\n\t"
+          "setp.ne.b32 q, %1, 0;\n\t"
+          "@q or.b32 %0, %0, %2;\n\t"
+          "}\n"
+          : "+r"(wm[e >> 5])
+          : "r"((uint32_t)win), "r"(1u << (e & 31)));
+    }
     int cnt = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) cnt += (x[e] >= T && (e < FI * 4 || pvalid)) ? 1 : 0;
+    for (int w2 = 0; w2 < (E + 31) / 32; ++w2) cnt += __popc(wm[w2]);
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1021,12 +1047,22 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       if (lane >= o) incl += v;
     }
     uint32_t pos = hist_addr + 8u * (uint32_t)(incl - cnt);
+    const uint32_t nlane4 = ~lane4;                          // ~(lane4 + c) = ~lane4 - c
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const bool win = x[e] >= T && (e < FI * 4 || pvalid);
-      const uint32_t id = lane4 + (uint32_t)((e >> 2) * 128 + (e & 3));
-      st_shared_v2_if(pos, ~id, __float_as_uint(x[e]), win);
-      pos += win ? 8u : 0u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred q;\n\t"
+          ".reg .b32 t;\n\t"
+          "and.b32 t, %3, %4;\n\t"
+          "setp.ne.b32 q, t, 0;\n\t"
+          "@q st.shared.v2.u32 [%0], {%1, %2};\n\t"
+          "@q add.u32 %0, %0, 8;\n\t"
+          "}\n"
+          : "+r"(pos)
+          : "r"(nlane4 - (uint32_t)((e >> 2) * 128 + (e & 3))), "r"(__float_as_uint(x[e])), "r"(wm[e >> 5]),
+            "r"(1u << (e & 31))
+          : "memory");
     }
   } else {
     // ---- ties at T: every x > T wins, and the `need` lowest-index elements with x == T ----
