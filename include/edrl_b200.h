@@ -103,15 +103,17 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
 /* Fused training pass (TF32 / TF32H / F16S): forward block sums AND the bandwidth-independent part of the gradient in one
  * sweep over the Gram tiles of rows [row_begin, row_begin + row_count) -- a training step then visits every tile
  * once instead of 1.5 times (edrl_mmd_forward + edrl_mmd_backward).  Same math as code/MMD.py:16-72 + autograd:
- *   U[i, :] = rowsum(G')_i z_i - (G' Z)_i,  G'_ij = -a_i a_j Q_ij / sigma_0
+ *   U[i, :] = -(G' Z)_i,  G'_ij = -a_i a_j Q_ij / sigma_0;  rowsum(G')_i goes to the workspace (apply_grad adds
+ *     rowsum(G')_i z_i)
  *     (the clamp mask [L_raw >= 0] of code/MMD.py:27 is not applied to G': a pair with L_raw < 0 is a numerical
  *      duplicate, z_i = z_j up to rounding, and its term G'_ij (z_i - z_j) vanishes whatever G'_ij is)
  *                                          -> U [edrl_mmd_grad_slabs(...), rows, d], partial sums over column slabs
  *   partial sums (sum a_i a_j K_ij, sum a_i a_j L_ij Q_ij over the rows of this call) are ADDED into the
  *   workspace accumulators; finalize != 0 (the call covers all rows): loss / stats are written as by
  *   edrl_mmd_forward; finalize == 0 (row-block sharded): they are returned in `partial` for the all-reduce.
- * edrl_mmd_apply_grad then yields dZ = grad_out * sign(M) * 4 * (U + c n z_i): the uniform bandwidth term c of G
- * in closed form (sum_j c (z_i - z_j) = c n z_i for centred Z).  dZ may alias U.  An optional second row range
+ * edrl_mmd_apply_grad then yields dZ = grad_out * sign(M) * 4 * (U + (rowsum(G')_i + c n) z_i - c sum_j z_j): the
+ * uniform bandwidth term c of G in closed form (sum_j c (z_i - z_j) = c n z_i - c sum_j z_j, with the column sums of
+ * the rounded centred operand).  dZ may alias U.  An optional second row range
  * (row_count2 > 0, after the first) lets a rank of a sharded evaluation cover its source rows and its target rows
  * in one launch; U / dZ hold range 1's rows followed by range 2's. */
 /* Number of partial output slabs the fused pass may write for row_count + row_count2 output rows: the row panels that
