@@ -77,25 +77,25 @@ class RawMMD:
         return dz
 
 
-def raw_forward_grad(raw, x, y, r0, c0, r1=0, c1=0, finalize=1, mul=2.0, num=5, ws=None):
+def raw_forward_grad(raw, x, y, r0, c0, r1=0, c1=0, finalize=1, mul=2.0, num=5, ws=None, flags=0):
     """edrl_mmd_forward_grad through the C-ABI: returns (loss, stats, partial, U, ws)."""
-    ws = ws or raw.workspace(x.shape[0], y.shape[0], x.shape[1], 0)
+    ws = ws or raw.workspace(x.shape[0], y.shape[0], x.shape[1], flags)
     loss = torch.zeros((), device="cuda")
     stats = torch.zeros(8, device="cuda")
     partial = torch.zeros(2, dtype=torch.float64, device="cuda")
-    slabs = int(raw.lib.edrl_mmd_grad_slabs(x.shape[0], y.shape[0], x.shape[1], 0, c0, c1))
+    slabs = int(raw.lib.edrl_mmd_grad_slabs(x.shape[0], y.shape[0], x.shape[1], flags, c0, c1))
     u = torch.empty(slabs, c0 + c1, x.shape[1], device="cuda")
     st = raw.L.stream_and_device(x)
     raw.L.check(raw.lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), x.shape[0], y.shape[0], x.shape[1], mul, num,
-                                              0, r0, c0, r1, c1, finalize, loss.data_ptr(), stats.data_ptr(),
+                                              flags, r0, c0, r1, c1, finalize, loss.data_ptr(), stats.data_ptr(),
                                               partial.data_ptr(), u.data_ptr(), ws.ptr, ws.nbytes, st))
     return loss, stats, partial, u, ws
 
 
-def raw_apply_grad(raw, n_s, n_t, d, stats, u, ws, r0, c0, r1=0, c1=0, grad_out=1.0):
+def raw_apply_grad(raw, n_s, n_t, d, stats, u, ws, r0, c0, r1=0, c1=0, grad_out=1.0, flags=0):
     g = torch.full((), float(grad_out), device="cuda")
     dz = torch.empty_like(u[0])
     st = raw.L.stream_and_device(u)
-    raw.L.check(raw.lib.edrl_mmd_apply_grad(n_s, n_t, d, 0, stats.data_ptr(), g.data_ptr(), u.data_ptr(), r0, c0, r1, c1,
+    raw.L.check(raw.lib.edrl_mmd_apply_grad(n_s, n_t, d, flags, stats.data_ptr(), g.data_ptr(), u.data_ptr(), r0, c0, r1, c1,
                                             dz.data_ptr(), ws.ptr, ws.nbytes, st))
     return dz

@@ -297,6 +297,44 @@ def test_fused_pass_matches_separate_kernels_and_oracle(raw, ns, nt, d):
         np.testing.assert_allclose(dzp[c0:].cpu().numpy(), dz1[r1:r1 + c1].cpu().numpy(), rtol=0, atol=2e-5 * gmax)
 
 
+@pytest.mark.parametrize("ns,nt,d", [(5000, 4600, 700), (3000, 2500, 1100), (9600, 9400, 300)])
+@pytest.mark.parametrize("prec,flag", [("tf32", 0), ("tf32h", 2), ("f16s", 4)])
+def test_work_list_shapes_fused_vs_separate_kernels(raw, ns, nt, d, prec, flag):
+    """Shapes whose work list mixes whole panels, column slabs and several 512-column feature passes (two passes at
+    d = 700, three at 1100; 150 / 129 / 149 virtual panels on 74 SM pairs): the persistent fused sweep against the
+    independent forward + tile-recomputing backward kernels, and two disjoint row ranges against the whole."""
+    from gpu_util import raw_apply_grad, raw_forward_grad
+    g = torch.Generator(device="cuda").manual_seed(ns + d)
+    xd = torch.randn(ns, d, device="cuda", generator=g)
+    yd = torch.randn(nt, d, device="cuda", generator=g) * 1.2 + 0.1
+    n = ns + nt
+    loss0, stats0, _, ws0 = raw.forward(xd, yd, flags=0)
+    dz0 = raw.backward(ns, nt, d, stats0, ws0, 0, n, grad_out=1.5, flags=0)
+    ws = raw.workspace(ns, nt, d, flag)
+    loss1, stats1, _, u, ws1 = raw_forward_grad(raw, xd, yd, 0, n, ws=ws, flags=flag)
+    dz1 = raw_apply_grad(raw, ns, nt, d, stats1, u, ws1, 0, n, grad_out=1.5, flags=flag)
+    torch.cuda.synchronize()
+    assert np.isclose(loss1.item(), loss0.item(), rtol=2e-5), (loss1.item(), loss0.item())
+    gmax = dz0.abs().max().item()
+    assert (dz1 - dz0).abs().max().item() <= 2e-3 * gmax, (dz1 - dz0).abs().max().item() / gmax
+    # two row ranges (one rank of a 2-rank sharded evaluation) reproduce their rows of the whole
+    h_s, h_t = ns // 2 + 17, nt // 2 - 5
+    tot = torch.zeros(2, dtype=torch.float64, device="cuda")
+    pieces = []
+    for (r0, c0, r1, c1) in ((0, h_s, ns, h_t), (h_s, ns - h_s, ns + h_t, nt - h_t)):
+        wsp = raw.workspace(ns, nt, d, flag)
+        _, _, part, u2, ws2 = raw_forward_grad(raw, xd, yd, r0, c0, r1, c1, finalize=0, ws=wsp, flags=flag)
+        tot += part
+        pieces.append((r0, c0, r1, c1, u2, ws2))
+    l2, s2 = raw.finalize(tot, ns, nt, pieces[-1][5])
+    torch.cuda.synchronize()
+    assert np.isclose(l2.item(), loss1.item(), rtol=1e-6)
+    for (r0, c0, r1, c1, u2, ws2) in pieces:
+        dzp = raw_apply_grad(raw, ns, nt, d, s2, u2, ws2, r0, c0, r1, c1, grad_out=1.5, flags=flag)
+        assert (dzp[:c0] - dz1[r0:r0 + c0]).abs().max().item() <= 2e-5 * gmax
+        assert (dzp[c0:] - dz1[r1:r1 + c1]).abs().max().item() <= 2e-5 * gmax
+
+
 # ---------------------------------------------------------------- host-side robustness: layouts, dtypes, streams, graphs
 def test_noncontiguous_bf16_inputs_and_side_stream():
     import edrl_b200

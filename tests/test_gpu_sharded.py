@@ -54,7 +54,7 @@ def _worker(rank, world, port, nl, d, prec):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("prec", ["tf32", "3xtf32"])
+@pytest.mark.parametrize("prec", ["tf32", "3xtf32", "f16s"])
 def test_sharded_mk_mmd_nccl(prec):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), 320, 96, prec), nprocs=world, join=True)
