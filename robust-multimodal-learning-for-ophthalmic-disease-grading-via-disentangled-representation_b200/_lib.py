@@ -31,6 +31,7 @@ PROTOTYPES = {
     "edrl_mmd_backward": (c_int, [c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "edrl_mmd_grad_slabs": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "edrl_mmd_sweep_plan": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_int)]),
     "edrl_mmd_forward_grad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),

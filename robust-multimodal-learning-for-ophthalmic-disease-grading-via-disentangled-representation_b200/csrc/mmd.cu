@@ -2417,12 +2417,12 @@ struct SweepPlan {
   int pairs;        // persistent CTA pairs to launch: pair c takes items c, c + pairs, ...
 };
 
-static SweepPlan make_plan(const Layout &L, int row_count, int row_count2) {
+static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int sms_override = 0) {
   SweepPlan pl;
   pl.panels = (row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM;
   const int ny = (L.d_pad + P2_FEATS - 1) / P2_FEATS;
   pl.vpanels = pl.panels * ny;
-  int sms = device_sm_count();
+  int sms = sms_override > 0 ? sms_override : device_sm_count();
   if (sms <= 0) sms = 148;
   const int C = sms / 2 > 0 ? sms / 2 : 1;
   const int nG = L.n_pad / Q_GROUP;
@@ -2550,6 +2550,15 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
 int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2) {
   if (n_s <= 0 || n_t <= 0 || d <= 0 || row_count <= 0 || row_count2 < 0) return 1;
   return make_plan(make_layout(n_s, n_t, d, flags), row_count, row_count2).split;
+}
+
+int edrl_mmd_sweep_plan(int n_s, int n_t, int d, int flags, int row_count, int row_count2, int sms, int *plan) {
+  EDRL_CHECK_ARG(plan && n_s > 0 && n_t > 0 && d > 0 && row_count > 0 && row_count2 >= 0, "MK_MMD sweep_plan: bad argument");
+  const Layout L = make_layout(n_s, n_t, d, flags);
+  const SweepPlan pl = make_plan(L, row_count, row_count2, sms);
+  plan[0] = pl.panels; plan[1] = pl.vpanels; plan[2] = pl.full_items; plan[3] = pl.split; plan[4] = pl.items;
+  plan[5] = pl.pairs; plan[6] = L.n_pad / Q_GROUP; plan[7] = L.d_pad;
+  return 0;
 }
 
 int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,

@@ -49,6 +49,50 @@ def test_workspace_bytes_is_pure_host_logic(pkg):
     assert 2 * 16384 * 512 * 4 <= big <= 2 * 16384 * 512 * 4 + (1 << 20)
 
 
+@pytest.mark.parametrize("ns,nt,d,rc,rc2,sms", [
+    (8192, 8192, 512, 16384, 0, 148),      # headline: 128 panels on 74 pairs -> 74 whole + 54 x 4 slabs
+    (65536, 65536, 1024, 131072, 0, 148),  # configs[3] on one GPU: 2 feature passes
+    (65536, 65536, 1024, 8192, 8192, 148), # one of 8 ranks: its source rows + its target rows
+    (64, 64, 3072, 128, 0, 148),           # the reference's training shape: 1 panel x 6 feature passes
+    (300, 212, 700, 512, 0, 148), (5000, 4600, 700, 9600, 0, 148), (1000, 24, 96, 1024, 0, 132),
+    (37, 53, 24, 17, 40, 148), (8192, 8192, 512, 16384, 0, 2)])
+@pytest.mark.parametrize("flags", [0, 2, 4])
+def test_sweep_work_list_covers_every_tile_once(pkg, ns, nt, d, rc, rc2, sms, flags):
+    """Host logic of the fused sweep (csrc/mmd.cu make_plan / sweep_item): every (virtual panel, column group) is swept
+    by exactly one work item, slabs are non-empty, the slab count is what edrl_mmd_grad_slabs reports, and splitting
+    never makes the critical path (items per CTA pair x groups) longer."""
+    import ctypes
+    lib = pkg._lib.load()
+    plan = (ctypes.c_int * 8)()
+    assert lib.edrl_mmd_sweep_plan(ns, nt, d, flags, rc, rc2, sms, plan) == 0
+    panels, vpanels, full, split, items, pairs, groups, d_pad = list(plan)
+    assert panels == -(-rc // 128) + -(-rc2 // 128)
+    assert vpanels == panels * -(-d_pad // 512) and d_pad >= d and d_pad % (128 if flags == 4 else 64) == 0
+    assert split in (1, 2, 4, 8) and split <= max(groups, 1)
+    assert items == full + (vpanels - full) * split and 1 <= pairs <= max(sms // 2, 1) and pairs <= items
+    seen = {}
+    load = [0] * pairs
+    for it in range(items):
+        if it < full:
+            vp, g0, g1 = it, 0, groups
+        else:
+            q = it - full
+            vp, s = full + q // split, q % split
+            g0, g1 = s * groups // split, (s + 1) * groups // split
+        assert 0 <= vp < vpanels and g0 < g1
+        for g in range(g0, g1):
+            assert (vp, g) not in seen
+            seen[(vp, g)] = it
+        load[it % pairs] += g1 - g0
+    assert len(seen) == vpanels * groups
+    unsplit = [0] * pairs
+    for vp in range(vpanels):
+        unsplit[vp % pairs] += groups
+    assert max(load) <= max(unsplit)
+    if sms == 148 and rc2 == 0:
+        assert split == lib.edrl_mmd_grad_slabs(ns, nt, d, flags, rc, rc2) or not __import__("torch").cuda.is_available()
+
+
 def test_sass_is_blackwell_native(pkg):
     """tcgen05 MMA / TMEM loads / TMA in the SASS of the shipped library (B200_PROFILING.md table)."""
     cuobjdump = "/usr/local/cuda/bin/cuobjdump"
