@@ -607,6 +607,37 @@ __device__ __forceinline__ void bitonic_step_reg(unsigned long long (&c)[4], int
   }
 }
 
+// the same network step on 32-bit composites (one shuffle and one min/max per element across lanes)
+template <int SIZE, int STRIDE>
+__device__ __forceinline__ void bitonic_step_reg32(uint32_t (&c)[4], int lane) {
+  if (STRIDE >= 4) {
+    const int lx = STRIDE >> 2;
+    const bool lower = (lane & lx) == 0;
+    const bool desc = (SIZE >= 128) ? true : ((lane & (SIZE >> 2)) == 0);
+    const bool keep_max = (lower == desc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, c[i], lx);
+      c[i] = keep_max ? max(c[i], o) : min(c[i], o);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((i & STRIDE) == 0) {
+        const int p = i | STRIDE;
+        bool desc;
+        if (SIZE == 2) desc = ((i & 2) == 0);
+        else if (SIZE == 4) desc = ((lane & 1) == 0);
+        else if (SIZE >= 128) desc = true;
+        else desc = ((lane & (SIZE >> 2)) == 0);
+        const uint32_t a = c[i], b = c[p];
+        const uint32_t hi = max(a, b), lo = min(a, b);
+        c[i] = desc ? hi : lo;
+        c[p] = desc ? lo : hi;
+      }
+    }
+  }
+}
 // order-preserving key with two integer ops: flip all bits of negatives, only the sign bit of the rest
 __device__ __forceinline__ uint32_t f2key_fast(float x) {
   const uint32_t u = __float_as_uint(x + 0.f);               // -0 -> +0: the two compare equal, so they must tie
@@ -1116,6 +1147,55 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
   float *vrow = vals + (size_t)r * k;
   int *irow = idx + (size_t)r * k;
   if (SORTED) {
+    // Fast path: 32-bit composites (key - key(T)) << 7 | (127 - slot) when the winners' keys span < 2^25 (about four
+    // binades above T): one shuffle and one min/max per element and step instead of a 64-bit compare-select.  Slots
+    // are in lane order, so equal keys would come out in the wrong order: any duplicate key among the winners (and a
+    // wider key range) falls through to the 64-bit key | ~index network below.
+    const uint32_t tkey = f2key_fast(T), xkey = f2key_fast(xmax);
+    bool sorted_done = false;
+    if (xkey - tkey < (1u << 25)) {
+      uint32_t c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sl = lane * 4 + i;
+        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
+        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
+      }
+      bitonic_step_reg32<2, 1>(c, lane);
+      bitonic_step_reg32<4, 2>(c, lane);   bitonic_step_reg32<4, 1>(c, lane);
+      bitonic_step_reg32<8, 4>(c, lane);   bitonic_step_reg32<8, 2>(c, lane);   bitonic_step_reg32<8, 1>(c, lane);
+      bitonic_step_reg32<16, 8>(c, lane);  bitonic_step_reg32<16, 4>(c, lane);  bitonic_step_reg32<16, 2>(c, lane);
+      bitonic_step_reg32<16, 1>(c, lane);
+      bitonic_step_reg32<32, 16>(c, lane); bitonic_step_reg32<32, 8>(c, lane);  bitonic_step_reg32<32, 4>(c, lane);
+      bitonic_step_reg32<32, 2>(c, lane);  bitonic_step_reg32<32, 1>(c, lane);
+      bitonic_step_reg32<64, 32>(c, lane); bitonic_step_reg32<64, 16>(c, lane); bitonic_step_reg32<64, 8>(c, lane);
+      bitonic_step_reg32<64, 4>(c, lane);  bitonic_step_reg32<64, 2>(c, lane);  bitonic_step_reg32<64, 1>(c, lane);
+      bitonic_step_reg32<128, 64>(c, lane); bitonic_step_reg32<128, 32>(c, lane); bitonic_step_reg32<128, 16>(c, lane);
+      bitonic_step_reg32<128, 8>(c, lane);  bitonic_step_reg32<128, 4>(c, lane);  bitonic_step_reg32<128, 2>(c, lane);
+      bitonic_step_reg32<128, 1>(c, lane);
+      // duplicates: position p and p + 1 carry the same key (p < k - 1)
+      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
+      bool dup = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t nx = (i < 3) ? c[i + 1] : nxt0;
+        const bool last = (i == 3) && (lane == 31);
+        dup = dup || (!last && lane * 4 + i + 1 < k && (c[i] >> 7) == (nx >> 7));
+      }
+      if (!__any_sync(0xffffffffu, dup)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int p2 = lane * 4 + i;
+          if (p2 < k) {
+            const uint2 w = buf[127 - (int)(c[i] & 127u)];
+            vrow[p2] = __uint_as_float(w.y);
+            irow[p2] = (int)~w.x;
+          }
+        }
+        sorted_done = true;
+      }
+    }
+    if (!sorted_done) {
     // composites key | ~index (value bits -> order-preserving key; empty slots stay 0 = below every key; -0 and +0
     // get the same key so that they order by index)
     unsigned long long c4[4];
@@ -1145,6 +1225,7 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
         vrow[p2] = key2f((uint32_t)(c4[i] >> 32));
         irow[p2] = id;
       }
+    }
     }
   } else {
 #pragma unroll
