@@ -121,9 +121,10 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
  * U must hold slabs * (row_count + row_count2) * d floats; apply_grad sums the slabs a row was split into. */
 int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2);
 /* The work list behind it, for inspection and host-side tests (no device work; sms <= 0: the current device's SM count,
- * 148 without a device): plan[8] = { row panels, virtual panels (x 512-column feature passes), virtual panels swept
- * whole, column slabs of each later virtual panel, work items, persistent CTA pairs launched, 256-column groups per
- * sweep, padded feature count }.  Item i < plan[2] sweeps virtual panel i over all groups; item i >= plan[2] sweeps
+ * 148 without a device): plan[10] = { row panels, virtual panels (x feature passes), virtual panels swept whole, column
+ * slabs of each later virtual panel, work items, persistent clusters launched, 256-column groups per sweep, padded
+ * feature count, 1 if clusters are 4 CTAs (d_pad > 768: two MMA pairs share the S phase) else 0 (2 CTAs), feature
+ * columns per pass (1024 / 512) }.  Item i < plan[2] sweeps virtual panel i over all groups; item i >= plan[2] sweeps
  * virtual panel plan[2] + (i - plan[2]) / plan[3], slab s = (i - plan[2]) % plan[3], groups [s G / plan[3], (s+1) G / plan[3]). */
 int edrl_mmd_sweep_plan(int n_s, int n_t, int d, int flags, int row_count, int row_count2, int sms, int *plan);
 int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,

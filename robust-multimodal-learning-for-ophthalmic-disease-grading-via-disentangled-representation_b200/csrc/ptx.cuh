@@ -157,6 +157,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ uint4 ld_cluster_v4(uint32_t cluster_addr) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(cluster_addr)
+               : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(cluster_addr), "f"(v) : "memory");
 }
@@ -275,6 +283,17 @@ __device__ __forceinline__ void mma_commit_pair_elect(uint64_t *bar) {
       "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "h"((uint16_t)3)
+      : "memory");
+}
+// the same with an explicit CTA mask (a 4-CTA cluster holds two MMA pairs: ranks {0,1} and {2,3})
+__device__ __forceinline__ void mma_commit_mask_elect(uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit_elect(uint64_t *bar) {

@@ -63,13 +63,14 @@ def test_sweep_work_list_covers_every_tile_once(pkg, ns, nt, d, rc, rc2, sms, fl
     never makes the critical path (items per CTA pair x groups) longer."""
     import ctypes
     lib = pkg._lib.load()
-    plan = (ctypes.c_int * 8)()
+    plan = (ctypes.c_int * 10)()
     assert lib.edrl_mmd_sweep_plan(ns, nt, d, flags, rc, rc2, sms, plan) == 0
-    panels, vpanels, full, split, items, pairs, groups, d_pad = list(plan)
+    panels, vpanels, full, split, items, pairs, groups, d_pad, quad, pass_feats = list(plan)
     assert panels == -(-rc // 128) + -(-rc2 // 128)
-    assert vpanels == panels * -(-d_pad // 512) and d_pad >= d and d_pad % (128 if flags == 4 else 64) == 0
+    assert quad == (1 if d_pad > 768 else 0) and pass_feats == (1024 if quad else 512)
+    assert vpanels == panels * -(-d_pad // pass_feats) and d_pad >= d and d_pad % (128 if flags == 4 else 64) == 0
     assert split in (1, 2, 4, 8) and split <= max(groups, 1)
-    assert items == full + (vpanels - full) * split and 1 <= pairs <= max(sms // 2, 1) and pairs <= items
+    assert items == full + (vpanels - full) * split and 1 <= pairs <= max(sms // (4 if quad else 2), 1) and pairs <= items
     seen = {}
     load = [0] * pairs
     for it in range(items):
