@@ -612,7 +612,8 @@ def run_ours(args, rank, local_rank, world):
         peak = peaks["bf16_burst"] / 2.0          # kind::tf32 issues at half the bf16 rate
         flops_b = 2.0 * n * n * d                 # G.Z: the algorithmic backward contraction
         flops_f = 1.0 * n * n * d                 # unique Gram entries n(n+1)/2 x 2d
-        passes = math.ceil(d / 512)
+        # Gram sweeps per step: one per 512-column feature pass (pair kernel), per 1024-column pass for d > 768 (quad kernel)
+        passes = math.ceil(d / 1024) if d > 768 else math.ceil(d / 512)
         ach_b = flops_b / (b_ms * 1e-3) / 1e12
         ach_f = flops_f / (f_ms * 1e-3) / 1e12
         fwd_info = {"kernel": "prep + mmd_fwd_pair_kernel (loss only, e.g. under no_grad)", "ms": f_ms,
@@ -631,7 +632,8 @@ def run_ours(args, rank, local_rank, world):
                 peak = peaks["bf16_burst"]            # both contractions issue kind::f16 MMAs
             mode_id = {"tf32": 0, "tf32h": 1, "f16s": 2}[prec]
             roof = {"bound": "tensor",
-                    "kernel": f"mmd_sweep256_kernel<FAST, MODE={mode_id}> (forward sums + gradient, one persistent Gram sweep)",
+                    "kernel": (f"mmd_sweep_quad_kernel<FAST, MODE={mode_id}>" if d > 768 else f"mmd_sweep256_kernel<FAST, MODE={mode_id}>")
+                              + " (forward sums + gradient, one persistent Gram sweep)",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": (profiled_traffic(f"mmd_sweep256_kernel<1, {mode_id}>") if (N, d) == (8192, 512) else None),
                     "traffic_note": "DRAM bytes per launch (ncu, profiles/); algorithmic HBM bytes are 3 n d 4 = 96 MiB "
