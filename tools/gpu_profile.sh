@@ -14,6 +14,9 @@ echo "full capture rc=$?"
 python tools/run_sweep.py f16s > gpurun_out/plain_sweep_f16s.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mmd_sweep256 -s 2 -c 1 -o gpurun_out/prof_sweep_f16s -f python tools/run_sweep.py f16s > gpurun_out/ncu_sweep_f16s.log 2>&1
 echo "f16s capture rc=$?"
+python tools/run_sweep.py tf32 8192 1024 > gpurun_out/plain_sweep_quad.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:mmd_sweep_quad -s 2 -c 1 -o gpurun_out/prof_sweep_quad -f python tools/run_sweep.py tf32 8192 1024 > gpurun_out/ncu_sweep_quad.log 2>&1
+echo "quad capture rc=$?"
 python tools/run_topk.py > gpurun_out/plain_topk.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:topk_ -s 2 -c 2 -o gpurun_out/prof_topk_final -f python tools/run_topk.py > gpurun_out/ncu_topk.log 2>&1
 echo "topk capture rc=$?"

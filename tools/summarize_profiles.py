@@ -41,7 +41,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     summary = {}
     traffic = {}
-    for name in ("prof_mmd_final", "prof_sweep_f16s", "prof_topk_final"):
+    for name in ("prof_mmd_final", "prof_sweep_f16s", "prof_sweep_quad", "prof_topk_final"):
         rep = os.path.join(SRC, name + ".ncu-rep")
         if not os.path.isfile(rep):
             continue
