@@ -9,6 +9,7 @@ with fp64 block accumulators.
 """
 from __future__ import annotations
 
+import functools
 import os
 
 import torch
@@ -64,11 +65,23 @@ def _check_inputs(source, target):
         raise RuntimeError("source and target must be on the same CUDA device")
 
 
+@functools.lru_cache(maxsize=256)
+def _workspace_bytes(n_s, n_t, d, flags):
+    return int(_lib.load().edrl_mmd_workspace_bytes(n_s, n_t, d, flags))
+
+
+@functools.lru_cache(maxsize=256)
+def _grad_slabs(n_s, n_t, d, flags, row_count, row_count2, device_index):
+    # (host arithmetic on the shape and the device's SM count: cached per shape and device -- small problems are bound by
+    #  host time, every ctypes call counts)
+    return int(_lib.load().edrl_mmd_grad_slabs(n_s, n_t, d, flags, row_count, row_count2))
+
+
 class Workspace:
     """1024-byte aligned scratch for one loss evaluation (shared by forward and backward)."""
 
     def __init__(self, n_s, n_t, d, flags, device):
-        self.nbytes = int(_lib.load().edrl_mmd_workspace_bytes(n_s, n_t, d, flags))
+        self.nbytes = _workspace_bytes(n_s, n_t, d, flags)
         if self.nbytes == 0:
             raise ValueError(f"MK_MMD: empty input (n_s={n_s} n_t={n_t} d={d})")
         self.buf = torch.empty(self.nbytes + 1024, dtype=torch.uint8, device=device)
@@ -91,7 +104,7 @@ class _MKMMDFunction(torch.autograd.Function):
         ctx.U = None
         if _FUSED and flags in _FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
             # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
-            slabs = int(lib.edrl_mmd_grad_slabs(n_s, n_t, d, flags, n_s + n_t, 0))
+            slabs = _grad_slabs(n_s, n_t, d, flags, n_s + n_t, 0, x.device.index)
             u = torch.empty(slabs, n_s + n_t, d, dtype=torch.float32, device=x.device)
             _lib.check(lib.edrl_mmd_forward_grad(x.data_ptr(), y.data_ptr(), n_s, n_t, d, float(kernel_mul),
                                                  int(kernel_num), flags, 0, n_s + n_t, 0, 0, 1, loss.data_ptr(),

@@ -98,7 +98,7 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         if _mmd._FUSED and flags in _mmd._FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
             # fused pass over this rank's rows (source rows, then target rows): partial sums + gradient part U
             (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
-            slabs = int(lib.edrl_mmd_grad_slabs(plan.n_s, plan.n_t, d, flags, c0, c1))
+            slabs = _mmd._grad_slabs(plan.n_s, plan.n_t, d, flags, c0, c1, x_all.device.index)
             u = torch.empty(slabs, c0 + c1, d, dtype=torch.float32, device=x_all.device)
             _lib.check(lib.edrl_mmd_forward_grad(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
                                                  float(kernel_mul), int(kernel_num), flags, r0, c0, r1, c1, 0, None,

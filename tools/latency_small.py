@@ -18,7 +18,7 @@ for (N, d) in ((64, 3072), (256, 512), (64, 512)):
     ws = Workspace(N, N, d, 0, x.device)
     loss = torch.empty((), device="cuda"); stats = torch.empty(8, device="cuda")
     st = _lib.stream_and_device(x); n = 2 * N
-    g = torch.ones((), device="cuda"); dz = torch.empty(n, d, device="cuda"); u = torch.empty(n, d, device="cuda")
+    g = torch.ones((), device="cuda"); dz = torch.empty(n, d, device="cuda"); u = torch.empty(8 * n, d, device="cuda")
     def timeit(name, fn):
         for _ in range(5): fn()
         torch.cuda.synchronize(); t0 = time.perf_counter()
