@@ -910,7 +910,7 @@ struct BwdParams {
   const float *stats;
   const float *grad_out;
   float *dz;                       // [row_count, d]
-  // fused forward + gradient pass (mmd_bwd_pair_kernel<.., FUSED = true>)
+  // fused forward + gradient pass (mmd_sweep256_kernel / mmd_sweep_quad_kernel)
   double *acc;                     // [0] M, [1] sum a a L Q, [2] sum r (from prep)
   unsigned *ticket;
   double *partial;                 // optional: partial sums out (sharded evaluation)
@@ -1295,16 +1295,13 @@ struct Bwd2Ctrl {
   float2 colinfo[2][BN];          // (r_j, a_j) per S stage; re-used for the row-sum exchange after the J loop
   float negc[MAX_KERNELS];
   float w[MAX_KERNELS];
-  double red[8][2];               // FUSED: per-warp partial block sums
 };
 static_assert(sizeof(Bwd2Ctrl) <= P2_CTRL_BYTES, "Bwd2Ctrl does not fit its smem slot");
 static_assert(Bwd2Cfg<0>::SMEM_BYTES <= 232448 && Bwd2Cfg<8>::SMEM_BYTES <= 232448, "smem budget");
 
-// FUSED: the same pass also evaluates the forward block sums (M, D) in the epilogue and writes the
-// bandwidth-independent part of the gradient U_i = rowsum(G')_i z_i - (G' Z)_i with G' = -a_i a_j Q_ij / sigma_0 [L_raw >= 0];
-// the uniform term c of G is applied afterwards in closed form (edrl_mmd_apply_grad): sum_j c (z_i - z_j) = c n z_i
-// for centred Z.  A training step then touches every Gram tile once instead of 1.5 times (forward + backward).
-template <bool FAST, int RES, bool FUSED>
+// (The fused forward + gradient training pass lives in mmd_sweep256_kernel / mmd_sweep_quad_kernel below; this kernel is
+// the separate backward of edrl_mmd_backward and the independent cross-check of the sweep in the tests.)
+template <bool FAST, int RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
 mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_zt,
                     const BwdParams p) {
@@ -1525,9 +1522,8 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const int j0 = jh * 64 + ch * 32;        // first of this thread's 32 columns inside the J tile
     const int gi = row_base + (int)rank * 64 + r;
 
-    const double sum_r = FUSED ? p.acc[2] : 0.0;
-    const float sigma0 = FUSED ? (float)bandwidth_sigma0(sum_r, p.n, p.mul, p.num) : p.stats[EDRL_MMD_STAT_SIGMA0];
-    const float cval = FUSED ? 0.f : p.stats[EDRL_MMD_STAT_C];
+    const float sigma0 = p.stats[EDRL_MMD_STAT_SIGMA0];
+    const float cval = p.stats[EDRL_MMD_STAT_C];
     float sig_last = sigma0;
     for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
     const float negc_last = -LOG2E / sig_last;
@@ -1538,11 +1534,6 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const float nai_sig = -ai / sigma0;
     const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
     float rowsum = 0.f;
-    // FUSED: forward block sums over this thread's row; rows outside [row_begin, row_begin + row_count) belong to
-    // another call (sharded evaluation), and only the first feature pass counts
-    const bool count_row = FUSED && blockIdx.y == 0 && (gi - rng_begin) < rng_count && gi < p.n;
-    const float ai_m = count_row ? ai : 0.f;
-    double accM = 0.0, accD = 0.0;
 
     for (int J = 0; J < nJ; ++J) {
       const int b = J & 1;
@@ -1559,7 +1550,6 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 64 + ch * 32), v);
       tmem_ld_wait();
       float g[32];
-      float tM = 0.f, tD = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float2 ci = ctl->colinfo[b][j0 + j];
@@ -1567,20 +1557,11 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         const float L = fmaxf(Lraw, 0.f);
         float K, Q;
         kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
-        if (FUSED) {
-          tM = fmaf(ci.y, K, tM);
-          tD = fmaf(ci.y * L, Q, tD);
-        }
-        float gv = FUSED ? (ci.y * Q) * nai_sig
-                         : fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);   // a_j == 0 <=> padded column
+        float gv = fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);   // a_j == 0 <=> padded column
         gv = (Lraw >= 0.f) ? gv : 0.f;
         const float gh = to_tf32(gv);
         g[j] = gh;
         rowsum += gh;
-      }
-      if (FUSED) {
-        accM += (double)(ai_m * tM);
-        accD += (double)(ai_m * tD);
       }
       // this thread's 32 values of row r go to K-atom (j0 / 32) of the B operand, 128-byte swizzle
       uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
@@ -1594,41 +1575,6 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       if (lane == 0) {
         mbar_arrive_cluster(g_full_leader);
         mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->s_empty[b]), 0));
-      }
-    }
-    if (FUSED && blockIdx.y == 0) {
-      // ---- forward block sums: warp -> CTA -> global (f64 atomics), last CTA finalises ----
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        accM += __shfl_xor_sync(0xffffffffu, accM, o);
-        accD += __shfl_xor_sync(0xffffffffu, accD, o);
-      }
-      if (lane == 0) {
-        ctl->red[ew][0] = accM;
-        ctl->red[ew][1] = accD;
-      }
-      named_barrier_sync(1, BWD_EPI_THREADS);
-      if (et == 0) {
-        double m = 0.0, dd = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          m += ctl->red[k][0];
-          dd += ctl->red[k][1];
-        }
-        atomicAdd(p.acc + 0, m);
-        atomicAdd(p.acc + 1, dd);
-        __threadfence();
-        const unsigned t = atomicAdd(p.ticket, 1u);
-        if (t == gridDim.x * gridDim.z - 1) {
-          __threadfence();
-          const double Mv = atomicAdd(p.acc + 0, 0.0);
-          const double Ds = atomicAdd(p.acc + 1, 0.0);
-          if (p.partial) {
-            p.partial[0] = Mv;
-            p.partial[1] = Ds;
-          }
-          if (p.finalize) write_final_stats(Mv, Ds, sum_r, p.n, p.mul, p.num, p.loss, p.stats_out);
-        }
       }
     }
     // ---- row sums of G: 4 partials per row (2 column halves x 2 lane halves) -> all 128 rows in both CTAs ----
@@ -1653,12 +1599,9 @@ mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
     const int ch = ew >> 2;
     const int tl = lg * 32 + lane;                           // feature lane of the M-tile
     const float *rs_all = reinterpret_cast<const float *>(&ctl->colinfo[1][0]);
-    float coef = 1.f;                                        // FUSED: U is written unscaled
-    if (!FUSED) {
-      const float M = p.stats[EDRL_MMD_STAT_M];
-      const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
-      coef = 4.f * sgn * p.grad_out[0];
-    }
+    const float M = p.stats[EDRL_MMD_STAT_M];
+    const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
+    const float coef = 4.f * sgn * p.grad_out[0];
     int rows_here = rng_count - lpanel * BM;
     if (rows_here > BM) rows_here = BM;
     if (p.n - row_base < rows_here) rows_here = p.n - row_base;
@@ -2969,11 +2912,11 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
   }
 }
 
-template <bool FAST, int RES, bool FUSED = false>
+template <bool FAST, int RES>
 static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt, const BwdParams &p, dim3 grid,
                              cudaStream_t st) {
   using Cfg = Bwd2Cfg<RES>;
-  auto kern = mmd_bwd_pair_kernel<FAST, RES, FUSED>;
+  auto kern = mmd_bwd_pair_kernel<FAST, RES>;
   // per launch (cheap): the attribute is per device, a process may drive several
   EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_z64, tm_zt, p);
