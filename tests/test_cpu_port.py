@@ -44,3 +44,27 @@ def test_cpu_port_eprl_matches_oracle():
     np.testing.assert_allclose(dz.numpy(), bw["dz"], rtol=1e-7, atol=1e-13)
     sig = 1.0 / (1.0 + np.exp(-prox[:, f:]))
     np.testing.assert_allclose(dprox.numpy(), np.concatenate([bw["dmu"], bw["dsigma"] * sig], 1), rtol=1e-7, atol=1e-13)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) prints one JSON line with the contract's
+    keys, the same metric / unit / config as our arm, and never touches a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["unit"] == "samples/s" and j["higher_is_better"] is True
+    assert j["config"]["N_per_side"] == 8192 and j["config"]["d"] == 512 and j["vs_baseline"] is None
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
