@@ -1043,12 +1043,12 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     return;
   }
   __syncwarp();
-  {
+  if (SORTED) {                                              // the sort reads all 128 slots: empty ones must be 0
     uint4 *b4 = reinterpret_cast<uint4 *>(hist);
     b4[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
     b4[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
   }
-  __syncwarp();
   const uint32_t lane4 = (uint32_t)lane << 2;
   if (exact) {
     // ---- lane-local compaction: every x >= T wins ----
