@@ -859,13 +859,18 @@ __device__ __noinline__ void radix_select_row_slow(const Rows &rows, int r, int 
 // of them take radix_select_row (the integer-key select above) instead.  Comparisons are on float values: -0 and +0
 // tie (lowest index first), as in torch.topk.
 // FI: full iterations (W / 128), PARTIAL: one more with lanes < (W / 4) % 32.
-constexpr int TV_HIST = 264;                  // 256 bins + overflow / dummy bins (16-byte aligned rows)
+constexpr int TV_LCAP = 8;                    // threshold-bin values a lane may hold before the row takes the slow path
+constexpr int TV_HIST = 264;                  // winners' buffer: 128 x 8 bytes; also bins + overflow / dummy bins
 constexpr int TV_CSTRIDE = 33;                // words per lane of the candidate staging area (a bin taken here holds <= 32; odd)
 template <int FI, bool PARTIAL, bool SORTED, class Rows>
 __global__ void __launch_bounds__(128, (FI <= 6 && !SORTED) ? 8 : 4)
 topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
   constexpr int NI = FI + (PARTIAL ? 1 : 0);
   constexpr int E = NI * 4;
+  // value bins of the histogram pass: about one threshold-bin candidate per 50 row elements keeps the ranked list short
+  // (<= 32), while fewer bins mean fewer distinct (bin, bank) pairs per warp increment -- the select is bound by
+  // shared-memory wavefronts
+  constexpr int BINS = (NI <= 7) ? 64 : ((NI <= 14) ? 128 : 256);
   __shared__ __align__(16) unsigned int s_hist[4][TV_HIST];  // per warp: histogram, later 128 64-bit winners
   __shared__ unsigned int s_cand[4][32 * TV_CSTRIDE];        // per warp: lane-local candidate lists, then the compact list
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -923,28 +928,30 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     // ---- one histogram pass over value bins: bin(x) = round((x - xmin) * 255 / range) in [0, 255] ----
     // y = (x - xmin) scale + 2^23 in [2^23, 2^23 + 255.5): bin = y's low bits.  (x - xmin >= 0 exactly; folding xmin into
     // the addend would round it to an integer and push the smallest values below 2^23.)
-    const float scale = 255.f / range;
+    const float scale = (float)(BINS - 1) / range;
     const float off = 8388608.f;
-    reinterpret_cast<uint4 *>(hist)[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
-    reinterpret_cast<uint4 *>(hist)[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
-    if (lane < 2) reinterpret_cast<uint4 *>(hist)[64 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = lane; i < (BINS + 8) / 4; i += 32) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
-    const uint32_t dummy = hist_addr + 260u * 4u;
+    const uint32_t dummy = hist_addr + (uint32_t)(BINS + 4) * 4u;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const uint32_t yb = __float_as_uint(fmaf(x[e] - xmin, scale, off));
-      uint32_t addr = hist_addr + ((yb & 0x1ffu) << 2);      // (rounding may reach bin 256: counted, scanned as bin 255)
+      uint32_t addr = hist_addr + ((yb & (uint32_t)(2 * BINS - 1)) << 2);   // (rounding may reach bin BINS: counted apart)
       if (e >= FI * 4) addr = pvalid ? addr : dummy;
       asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
     }
     __syncwarp();
-    // lane l owns bins 8 (31 - l) .. 8 (31 - l) + 7, walked from the top: lane 0 holds the 8 largest
-    const int base = (31 - lane) * 8;
-    const uint4 hlo = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2];
-    const uint4 hhi = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2 + 1];
-    int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
-    const int over = (int)hist[256];                         // bin 256 (fp rounding at the very top): above bin 255
-    const int t = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    // lane l owns bins BPL (31 - l) .. BPL (31 - l) + BPL - 1, walked from the top: lane 0 holds the largest
+    constexpr int BPL = BINS / 32;
+    const int base = (31 - lane) * BPL;
+    int c[BPL];
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < BPL; ++i) {
+      c[i] = (int)hist[base + BPL - 1 - i];
+      t += c[i];
+    }
+    const int over = (int)hist[BINS];                     // bin BINS (fp rounding at the very top): above the last
     int incl = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -960,10 +967,10 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       int bn = 0, cb = 0;
       bool found = false;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < BPL; ++i) {
         if (!found) {
           if (c[i] >= rem) {
-            bn = base + 7 - i;
+            bn = base + BPL - 1 - i;
             cb = c[i];
             found = true;
           } else {
@@ -1004,17 +1011,17 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
         const int v = __shfl_up_sync(0xffffffffu, cincl, o);
         if (lane >= o) cincl += v;
       }
-      const uint32_t more = __ballot_sync(0xffffffffu, mycnt > 4);
+      const uint32_t more = __ballot_sync(0xffffffffu, mycnt > TV_LCAP);
       if (more == 0u) {
         __syncwarp();
-        uint32_t mk[4];
+        uint32_t mk[TV_LCAP];
 #pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2) mk[c2] = (c2 < mycnt) ? mine[c2] : 0u;
+        for (int c2 = 0; c2 < TV_LCAP; ++c2) mk[c2] = (c2 < mycnt) ? mine[c2] : 0u;
         __syncwarp();
         unsigned int *clist = s_cand[wib];                   // compact list (overwrites the lane lists: read first)
         const int coff = cincl - mycnt;
 #pragma unroll
-        for (int c2 = 0; c2 < 4; ++c2)
+        for (int c2 = 0; c2 < TV_LCAP; ++c2)
           if (c2 < mycnt) clist[coff + c2] = mk[c2];
         __syncwarp();
         const float ci = (lane < cntb) ? __uint_as_float(clist[lane]) : 0.f;
