@@ -933,10 +933,13 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     for (int i = lane; i < (BINS + 8) / 4; i += 32) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
     const uint32_t dummy = hist_addr + (uint32_t)(BINS + 4) * 4u;
+    // y's bits are 0x4b000000 + bin (bin <= BINS: rounding may reach one past the last, counted apart), so the bin's
+    // address is one shift-add away: 4 y + (hist - 4 * 0x4b000000) in 32-bit wrap-around arithmetic
+    const uint32_t hbase = hist_addr - (0x4b000000u << 2);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const uint32_t yb = __float_as_uint(fmaf(x[e] - xmin, scale, off));
-      uint32_t addr = hist_addr + ((yb & (uint32_t)(2 * BINS - 1)) << 2);   // (rounding may reach bin BINS: counted apart)
+      uint32_t addr = (yb << 2) + hbase;
       if (e >= FI * 4) addr = pvalid ? addr : dummy;
       asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
     }
@@ -992,16 +995,19 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
       const uint32_t lp0 = lp;
 #pragma unroll
       for (int e = 0; e < E; ++e) {
-        const bool in = (__float_as_uint(fmaf(x[e] - xmin, scale, off)) == ytarget) && (e < FI * 4 || pvalid);
+        // (compare, predicated store and predicated pointer bump in one asm block: passing a bool in costs a select and
+        //  a second compare per element)
+        const uint32_t yb = __float_as_uint(fmaf(x[e] - xmin, scale, off));
+        const uint32_t yt = (e < FI * 4 || pvalid) ? ytarget : 0u;         // never equal for lanes without data
         asm volatile(
             "{\n\t"
             ".reg .pred q;\n\t"
-            "setp.ne.b32 q, %2, 0;\n\t"
+            "setp.eq.u32 q, %2, %3;\n\t"
             "@q st.shared.b32 [%0], %1;\n\t"
             "@q add.u32 %0, %0, 4;\n\t"
             "}\n"
             : "+r"(lp)
-            : "r"(__float_as_uint(x[e])), "r"((uint32_t)in)
+            : "r"(__float_as_uint(x[e])), "r"(yb), "r"(yt)
             : "memory");
       }
       const int mycnt = (int)((lp - lp0) >> 2);
@@ -1066,14 +1072,15 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     for (int w2 = 0; w2 < (E + 31) / 32; ++w2) wm[w2] = 0u;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-      const bool win = x[e] >= T && (e < FI * 4 || pvalid);
+      // lanes without data in the partial iteration compare against +inf (rows here are finite: never true)
+      const float te = (e < FI * 4 || pvalid) ? T : __int_as_float(0x7f800000);
       asm("{\n\t"
           ".reg .pred q;\n\t"
-          "setp.ne.b32 q, %1, 0;\n\t"
-          "@q or.b32 %0, %0, %2;\n\t"
+          "setp.ge.f32 q, %1, %2;\n\t"
+          "@q or.b32 %0, %0, %3;\n\t"
           "}\n"
           : "+r"(wm[e >> 5])
-          : "r"((uint32_t)win), "r"(1u << (e & 31)));
+          : "f"(x[e]), "f"(te), "r"(1u << (e & 31)));
     }
     int cnt = 0;
 #pragma unroll
