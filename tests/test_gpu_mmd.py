@@ -335,6 +335,34 @@ def test_work_list_shapes_fused_vs_separate_kernels(raw, ns, nt, d, prec, flag):
         assert (dzp[c0:] - dz1[r1:r1 + c1]).abs().max().item() <= 2e-5 * gmax
 
 
+@pytest.mark.parametrize("prec,flag", [("tf32", 0), ("tf32h", 2), ("f16s", 4)])
+@pytest.mark.parametrize("ns,nt,d", [(700, 650, 1100), (900, 1100, 400)])
+def test_generic_bandwidths_in_the_sweeps(raw, ns, nt, d, prec, flag):
+    """kernel_mul != 2 / kernel_num != 5 take the generic exponential path of the epilogue: the quad sweep (d = 1100) and
+    the pair sweep (d = 400) against the separate kernels and the fp64 oracle."""
+    from gpu_util import raw_apply_grad, raw_forward_grad
+    rng = np.random.default_rng(ns + d)
+    x = rng.standard_normal((ns, d)).astype(np.float32)
+    y = (rng.standard_normal((nt, d)) * 1.3 - 0.2).astype(np.float32)
+    xd, yd = dev(x), dev(y)
+    n = ns + nt
+    for (mul, num) in ((1.5, 3), (3.0, 7)):
+        loss0, stats0, _, ws0 = raw.forward(xd, yd, mul=mul, num=num, flags=0)
+        dz0 = raw.backward(ns, nt, d, stats0, ws0, 0, n, grad_out=0.5, mul=mul, num=num, flags=0)
+        ws = raw.workspace(ns, nt, d, flag)
+        loss1, stats1, _, u, ws1 = raw_forward_grad(raw, xd, yd, 0, n, mul=mul, num=num, ws=ws, flags=flag)
+        dz1 = raw_apply_grad(raw, ns, nt, d, stats1, u, ws1, 0, n, grad_out=0.5, flags=flag)
+        torch.cuda.synchronize()
+        assert np.isclose(loss1.item(), loss0.item(), rtol=2e-5), (mul, num)
+        gmax = dz0.abs().max().item()
+        assert (dz1 - dz0).abs().max().item() <= 2e-3 * gmax, (mul, num)
+        ref, _, dx, dy = O.mk_mmd_grad(x.astype(np.float64), y.astype(np.float64), kernel_mul=mul, kernel_num=num,
+                                       grad_out=0.5)
+        assert np.isclose(loss1.item(), ref, rtol=1e-3, atol=1e-6), (mul, num)
+        gm = max(np.abs(dx).max(), np.abs(dy).max())
+        assert np.abs(dz1.cpu().numpy() - np.concatenate([dx, dy])).max() <= 2e-3 * gm, (mul, num)
+
+
 # ---------------------------------------------------------------- host-side robustness: layouts, dtypes, streams, graphs
 def test_noncontiguous_bf16_inputs_and_side_stream():
     import edrl_b200
