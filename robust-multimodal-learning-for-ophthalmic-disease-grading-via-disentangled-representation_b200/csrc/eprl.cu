@@ -9,6 +9,7 @@
 //   K8  proxy_loss_fwd / select_loss_bwd      : loss and its scatter backward (B6/B7)
 //   K9  gather_rows_{fwd,bwd}                 : feature gather by index (north-star extension)
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 
 #include "../../include/edrl_b200.h"
@@ -638,6 +639,41 @@ __device__ __forceinline__ void bitonic_step_reg32(uint32_t (&c)[4], int lane) {
     }
   }
 }
+// the whole descending network for 32 NPL composites, NPL (1 or 2) per lane at positions lane * NPL + i: small k
+template <int NPL>
+__device__ __forceinline__ void bitonic_sort_desc32(uint32_t (&c)[NPL], int lane) {
+  constexpr int TOT = 32 * NPL;
+#pragma unroll
+  for (int size = 2; size <= TOT; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= NPL) {
+        const int lx = stride / NPL;
+        const bool lower = (lane & lx) == 0;
+        const bool desc = (size >= TOT) ? true : (((lane * NPL) & size) == 0);
+        const bool keep_max = (lower == desc);
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const uint32_t o = __shfl_xor_sync(0xffffffffu, c[i], lx);
+          c[i] = keep_max ? max(c[i], o) : min(c[i], o);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          if ((i & stride) == 0) {
+            const int p2 = i | stride;
+            const bool desc = (size >= TOT) ? true : (((lane * NPL + i) & size) == 0);
+            const uint32_t a = c[i], b = c[p2];
+            const uint32_t hi = max(a, b), lo = min(a, b);
+            c[i] = desc ? hi : lo;
+            c[p2] = desc ? lo : hi;
+          }
+        }
+      }
+    }
+  }
+}
+
 // order-preserving key with two integer ops: flip all bits of negatives, only the sign bit of the rest
 __device__ __forceinline__ uint32_t f2key_fast(float x) {
   const uint32_t u = __float_as_uint(x + 0.f);               // -0 -> +0: the two compare equal, so they must tie
@@ -1167,7 +1203,42 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     // wider key range) falls through to the 64-bit key | ~index network below.
     const uint32_t tkey = f2key_fast(T), xkey = f2key_fast(xmax);
     bool sorted_done = false;
-    if (xkey - tkey < (1u << 25)) {
+    auto small_sort = [&](auto npl_tag) {                    // k <= 32 NPL: NPL composites per lane
+      constexpr int NPL = decltype(npl_tag)::value;
+      uint32_t c[NPL];
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int sl = lane * NPL + i;
+        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
+        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
+      }
+      bitonic_sort_desc32<NPL>(c, lane);
+      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
+      bool dup = false;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const uint32_t nx = (i < NPL - 1) ? c[(i + 1) % NPL] : nxt0;
+        const bool last = (i == NPL - 1) && (lane == 31);
+        dup = dup || (!last && lane * NPL + i + 1 < k && (c[i] >> 7) == (nx >> 7));
+      }
+      if (__any_sync(0xffffffffu, dup)) return false;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int p2 = lane * NPL + i;
+        if (p2 < k) {
+          const uint2 w = buf[127 - (int)(c[i] & 127u)];
+          vrow[p2] = __uint_as_float(w.y);
+          irow[p2] = (int)~w.x;
+        }
+      }
+      return true;
+    };
+    const bool narrow = xkey - tkey < (1u << 25);
+    if (narrow && k <= 32) {
+      sorted_done = small_sort(std::integral_constant<int, 1>{});
+    } else if (narrow && k <= 64) {
+      sorted_done = small_sort(std::integral_constant<int, 2>{});
+    } else if (narrow) {
       uint32_t c[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
