@@ -288,6 +288,29 @@ def essence_point_extras(peaks):
                                        "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
                                        "order": "selection set only (what the Essence-Point loss consumes)"}
         del x
+        # the rest of the scaled select sweep of SURVEY.md 8d (R x W x 4 bytes >= 256 MB each)
+        sweep = []
+        for (R2, W2) in ((1 << 17, 1600), (1 << 15, 8192), (1 << 20, 800)):
+            x2 = torch.randn(R2, W2, device="cuda")
+            row = {"rows": R2, "width": W2, "k": k}
+            for srt in (False, True):
+                for _ in range(2):
+                    edrl_b200.topk_rows(x2, k, sorted=srt)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    edrl_b200.topk_rows(x2, k, sorted=srt)
+                b.record()
+                torch.cuda.synchronize()
+                ms2 = a.elapsed_time(b) / 5
+                byts2 = R2 * W2 * 4 + R2 * k * 8
+                row["sorted" if srt else "unsorted"] = {"ms": ms2, "GB/s": byts2 / ms2 / 1e6,
+                                                        "frac_hbm": byts2 / ms2 / 1e6 / peaks["hbm_gbs"]}
+            sweep.append(row)
+            del x2
+        out["select_sweep"] = sweep
+        out["select_sweep_note"] = ("W <= 2048 (W % 4 == 0): one warp per row, topk_vec_kernel; W = 8192: the older one-block-"
+                                    "per-row radix kernel (not yet rebuilt around value bins)")
         B, T, D, kk = 4096, 216, 768, 32
         feat = torch.randn(B, T, D, device="cuda")
         idx = torch.stack([torch.randperm(T, device="cuda")[:kk] for _ in range(64)]).repeat(B // 64, 1).int()

@@ -3,7 +3,8 @@ import sys, torch
 sys.path.insert(0, ".")
 import edrl_b200
 peak = 6548.2
-for (R, W, k) in ((1 << 18, 800, 100), (1 << 17, 1600, 100), (1 << 18, 1024, 100), (1 << 20, 216, 32)):
+for (R, W, k) in ((1 << 18, 800, 100), (1 << 17, 1600, 100), (1 << 18, 1024, 100), (1 << 20, 216, 32), (1 << 15, 8192, 100),
+                  (1 << 10, 800, 100), (1 << 14, 800, 100), (1 << 20, 800, 100)):
     x = torch.randn(R, W, device="cuda")
     for s in (False, True):
         for _ in range(3):
