@@ -309,8 +309,8 @@ def essence_point_extras(peaks):
             sweep.append(row)
             del x2
         out["select_sweep"] = sweep
-        out["select_sweep_note"] = ("W <= 2048 (W % 4 == 0): one warp per row, topk_vec_kernel; W = 8192: the older one-block-"
-                                    "per-row radix kernel (not yet rebuilt around value bins)")
+        out["select_sweep_note"] = ("W <= 2048 (W % 4 == 0): one warp per row, topk_vec_kernel; 2048 < W <= 8192: one 256-thread "
+                                    "block per row, topk_vecblock_kernel")
         B, T, D, kk = 4096, 216, 768, 32
         feat = torch.randn(B, T, D, device="cuda")
         idx = torch.stack([torch.randperm(T, device="cuda")[:kk] for _ in range(64)]).repeat(B // 64, 1).int()

@@ -877,6 +877,140 @@ __device__ __noinline__ void radix_select_row_slow(const Rows &rows, int r, int 
   radix_select_row<E, false, SORTED, Rows>(rows, r, k, hist, lane, vals, idx);
 }
 
+// The winners of one row -- 64-bit (~index, value bits) pairs in buf[0, k), zeros behind them when SORTED -- to global
+// memory, by one warp: SORTED in torch.topk's order (descending value, ties by ascending index), else as they are.
+template <bool SORTED>
+__device__ __forceinline__ void emit_winners(uint2 *buf, int k, int lane, uint32_t tkey_in, uint32_t xkey_in,
+                                             float *__restrict__ vrow, int *__restrict__ irow) {
+  if (SORTED) {
+    // Fast path: 32-bit composites (key - key(T)) << 7 | (127 - slot) when the winners' keys span < 2^25 (about four
+    // binades above T): one shuffle and one min/max per element and step instead of a 64-bit compare-select.  Slots
+    // are in lane order, so equal keys would come out in the wrong order: any duplicate key among the winners (and a
+    // wider key range) falls through to the 64-bit key | ~index network below.
+    const uint32_t tkey = tkey_in, xkey = xkey_in;
+    bool sorted_done = false;
+    auto small_sort = [&](auto npl_tag) {                    // k <= 32 NPL: NPL composites per lane
+      constexpr int NPL = decltype(npl_tag)::value;
+      uint32_t c[NPL];
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int sl = lane * NPL + i;
+        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
+        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
+      }
+      bitonic_sort_desc32<NPL>(c, lane);
+      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
+      bool dup = false;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const uint32_t nx = (i < NPL - 1) ? c[(i + 1) % NPL] : nxt0;
+        const bool last = (i == NPL - 1) && (lane == 31);
+        dup = dup || (!last && lane * NPL + i + 1 < k && (c[i] >> 7) == (nx >> 7));
+      }
+      if (__any_sync(0xffffffffu, dup)) return false;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int p2 = lane * NPL + i;
+        if (p2 < k) {
+          const uint2 w = buf[127 - (int)(c[i] & 127u)];
+          vrow[p2] = __uint_as_float(w.y);
+          irow[p2] = (int)~w.x;
+        }
+      }
+      return true;
+    };
+    const bool narrow = xkey - tkey < (1u << 25);
+    if (narrow && k <= 32) {
+      sorted_done = small_sort(std::integral_constant<int, 1>{});
+    } else if (narrow && k <= 64) {
+      sorted_done = small_sort(std::integral_constant<int, 2>{});
+    } else if (narrow) {
+      uint32_t c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sl = lane * 4 + i;
+        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
+        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
+      }
+      bitonic_step_reg32<2, 1>(c, lane);
+      bitonic_step_reg32<4, 2>(c, lane);   bitonic_step_reg32<4, 1>(c, lane);
+      bitonic_step_reg32<8, 4>(c, lane);   bitonic_step_reg32<8, 2>(c, lane);   bitonic_step_reg32<8, 1>(c, lane);
+      bitonic_step_reg32<16, 8>(c, lane);  bitonic_step_reg32<16, 4>(c, lane);  bitonic_step_reg32<16, 2>(c, lane);
+      bitonic_step_reg32<16, 1>(c, lane);
+      bitonic_step_reg32<32, 16>(c, lane); bitonic_step_reg32<32, 8>(c, lane);  bitonic_step_reg32<32, 4>(c, lane);
+      bitonic_step_reg32<32, 2>(c, lane);  bitonic_step_reg32<32, 1>(c, lane);
+      bitonic_step_reg32<64, 32>(c, lane); bitonic_step_reg32<64, 16>(c, lane); bitonic_step_reg32<64, 8>(c, lane);
+      bitonic_step_reg32<64, 4>(c, lane);  bitonic_step_reg32<64, 2>(c, lane);  bitonic_step_reg32<64, 1>(c, lane);
+      bitonic_step_reg32<128, 64>(c, lane); bitonic_step_reg32<128, 32>(c, lane); bitonic_step_reg32<128, 16>(c, lane);
+      bitonic_step_reg32<128, 8>(c, lane);  bitonic_step_reg32<128, 4>(c, lane);  bitonic_step_reg32<128, 2>(c, lane);
+      bitonic_step_reg32<128, 1>(c, lane);
+      // duplicates: position p and p + 1 carry the same key (p < k - 1)
+      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
+      bool dup = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t nx = (i < 3) ? c[i + 1] : nxt0;
+        const bool last = (i == 3) && (lane == 31);
+        dup = dup || (!last && lane * 4 + i + 1 < k && (c[i] >> 7) == (nx >> 7));
+      }
+      if (!__any_sync(0xffffffffu, dup)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int p2 = lane * 4 + i;
+          if (p2 < k) {
+            const uint2 w = buf[127 - (int)(c[i] & 127u)];
+            vrow[p2] = __uint_as_float(w.y);
+            irow[p2] = (int)~w.x;
+          }
+        }
+        sorted_done = true;
+      }
+    }
+    if (!sorted_done) {
+    // composites key | ~index (value bits -> order-preserving key; empty slots stay 0 = below every key; -0 and +0
+    // get the same key so that they order by index)
+    unsigned long long c4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint2 w = buf[lane * 4 + i];
+      const uint32_t kk = (lane * 4 + i < k) ? f2key_fast(__uint_as_float(w.y)) : 0u;
+      c4[i] = ((unsigned long long)kk << 32) | w.x;
+    }
+    bitonic_step_reg<2, 1>(c4, lane);
+    bitonic_step_reg<4, 2>(c4, lane);   bitonic_step_reg<4, 1>(c4, lane);
+    bitonic_step_reg<8, 4>(c4, lane);   bitonic_step_reg<8, 2>(c4, lane);   bitonic_step_reg<8, 1>(c4, lane);
+    bitonic_step_reg<16, 8>(c4, lane);  bitonic_step_reg<16, 4>(c4, lane);  bitonic_step_reg<16, 2>(c4, lane);
+    bitonic_step_reg<16, 1>(c4, lane);
+    bitonic_step_reg<32, 16>(c4, lane); bitonic_step_reg<32, 8>(c4, lane);  bitonic_step_reg<32, 4>(c4, lane);
+    bitonic_step_reg<32, 2>(c4, lane);  bitonic_step_reg<32, 1>(c4, lane);
+    bitonic_step_reg<64, 32>(c4, lane); bitonic_step_reg<64, 16>(c4, lane); bitonic_step_reg<64, 8>(c4, lane);
+    bitonic_step_reg<64, 4>(c4, lane);  bitonic_step_reg<64, 2>(c4, lane);  bitonic_step_reg<64, 1>(c4, lane);
+    bitonic_step_reg<128, 64>(c4, lane); bitonic_step_reg<128, 32>(c4, lane); bitonic_step_reg<128, 16>(c4, lane);
+    bitonic_step_reg<128, 8>(c4, lane);  bitonic_step_reg<128, 4>(c4, lane);  bitonic_step_reg<128, 2>(c4, lane);
+    bitonic_step_reg<128, 1>(c4, lane);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p2 = lane * 4 + i;
+      if (p2 < k) {
+        const int id = (int)~(uint32_t)(c4[i] & 0xffffffffu);
+        vrow[p2] = key2f((uint32_t)(c4[i] >> 32));
+        irow[p2] = id;
+      }
+    }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t2 = lane + 32 * i;
+      if (t2 < k) {
+        const uint2 cc = buf[t2];
+        vrow[t2] = __uint_as_float(cc.y);
+        irow[t2] = (int)~cc.x;
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- K7b vectorised warp select
 // One warp per row, uniform row width W (a multiple of 4, rows 16-byte aligned), k <= 128.  The select is bound by
 // instruction issue and the integer pipe, not by HBM, so it is built around the instruction count:
@@ -1194,135 +1328,288 @@ topk_vec_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *_
     }
   }
   __syncwarp();
-  float *vrow = vals + (size_t)r * k;
-  int *irow = idx + (size_t)r * k;
-  if (SORTED) {
-    // Fast path: 32-bit composites (key - key(T)) << 7 | (127 - slot) when the winners' keys span < 2^25 (about four
-    // binades above T): one shuffle and one min/max per element and step instead of a 64-bit compare-select.  Slots
-    // are in lane order, so equal keys would come out in the wrong order: any duplicate key among the winners (and a
-    // wider key range) falls through to the 64-bit key | ~index network below.
-    const uint32_t tkey = f2key_fast(T), xkey = f2key_fast(xmax);
-    bool sorted_done = false;
-    auto small_sort = [&](auto npl_tag) {                    // k <= 32 NPL: NPL composites per lane
-      constexpr int NPL = decltype(npl_tag)::value;
-      uint32_t c[NPL];
+  emit_winners<SORTED>(buf, k, lane, f2key_fast(T), f2key_fast(xmax), vals + (size_t)r * k, idx + (size_t)r * k);
+}
+
+// ----------------------------------------------------------------------------- K7c vectorised block select (wide rows)
+// One 256-thread block per row for 2048 < W <= 8192 (uniform width, W % 4 == 0, 16-byte aligned rows, k <= 128): the
+// same plan as topk_vec_kernel with the row spread over 8 warps -- thread t holds float4 number i * 256 + t (i < NI4) in
+// registers; one histogram pass over 256 value bins in shared memory, the threshold bin's values collected and ranked
+// by warp 0, winners compacted through a per-thread win mask and a block prefix.  Rows with NaN / infinities, constant
+// rows and crowded threshold bins run the multi-pass radix select on order-preserving integer keys instead (same
+// registers, further histogram passes); ties at the threshold keep the lowest indices (an index-ordered block scan).
+constexpr int VB_THREADS = 256;
+struct VbCtl {
+  unsigned int cand_n, bin, cntb, rem, exact, tkey, need, pad;
+  unsigned int kmin[8], kmax[8], bad[8], wsum[8];
+};
+// exclusive prefix of v over the 256 threads of the block (and the block total); two barriers
+__device__ __forceinline__ int vb_excl_scan(int v, int &total, unsigned int *wsum, int warp, int lane) {
+  int incl = v;
 #pragma unroll
-      for (int i = 0; i < NPL; ++i) {
-        const int sl = lane * NPL + i;
-        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
-        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
-      }
-      bitonic_sort_desc32<NPL>(c, lane);
-      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
-      bool dup = false;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wsum[warp] = (unsigned int)incl;
+  __syncthreads();
+  int before = 0;
+  total = 0;
 #pragma unroll
-      for (int i = 0; i < NPL; ++i) {
-        const uint32_t nx = (i < NPL - 1) ? c[(i + 1) % NPL] : nxt0;
-        const bool last = (i == NPL - 1) && (lane == 31);
-        dup = dup || (!last && lane * NPL + i + 1 < k && (c[i] >> 7) == (nx >> 7));
-      }
-      if (__any_sync(0xffffffffu, dup)) return false;
+  for (int w = 0; w < 8; ++w) {
+    const int s = (int)wsum[w];
+    before += (w < warp) ? s : 0;
+    total += s;
+  }
+  __syncthreads();
+  return before + incl - v;
+}
+// warp 0: walk the 256-bin histogram from the top; the bin that holds the need-th largest, its count, and how many of
+// its values are wanted
+__device__ __forceinline__ void vb_scan_hist(const unsigned int *hist, int need, int lane, VbCtl *ctl) {
+  const int base = (31 - lane) * 8;
+  const uint4 hlo = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2];
+  const uint4 hhi = reinterpret_cast<const uint4 *>(hist)[(31 - lane) * 2 + 1];
+  const int c[8] = {(int)hhi.w, (int)hhi.z, (int)hhi.y, (int)hhi.x, (int)hlo.w, (int)hlo.z, (int)hlo.y, (int)hlo.x};
+  const int over = (int)hist[256];
+  const int t = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+  int incl = t;
 #pragma unroll
-      for (int i = 0; i < NPL; ++i) {
-        const int p2 = lane * NPL + i;
-        if (p2 < k) {
-          const uint2 w = buf[127 - (int)(c[i] & 127u)];
-          vrow[p2] = __uint_as_float(w.y);
-          irow[p2] = (int)~w.x;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  incl += over;
+  const uint32_t hit = __ballot_sync(0xffffffffu, incl >= need);
+  const int L = __ffs(hit) - 1;
+  if (L < 0) {                                               // (cannot happen for k <= W; leave a value that fails the checks)
+    if (lane == 0) { ctl->bin = 0; ctl->cntb = 0; ctl->rem = 0; }
+    return;
+  }
+  if (lane == L) {
+    int rem = need - (incl - t);
+    int bn = 0, cb = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (!found) {
+        if (c[i] >= rem) {
+          bn = base + 7 - i;
+          cb = c[i];
+          found = true;
+        } else {
+          rem -= c[i];
         }
       }
-      return true;
-    };
-    const bool narrow = xkey - tkey < (1u << 25);
-    if (narrow && k <= 32) {
-      sorted_done = small_sort(std::integral_constant<int, 1>{});
-    } else if (narrow && k <= 64) {
-      sorted_done = small_sort(std::integral_constant<int, 2>{});
-    } else if (narrow) {
-      uint32_t c[4];
+    }
+    ctl->bin = (unsigned int)bn;
+    ctl->cntb = (unsigned int)cb;
+    ctl->rem = (unsigned int)(rem > 0 ? rem : 0);
+  }
+}
+
+template <int NI4, bool SORTED, class Rows>
+__global__ void __launch_bounds__(VB_THREADS, 4)
+topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
+  constexpr int E = NI4 * 4;
+  static_assert(E <= 32, "one 32-bit win mask per thread");
+  __shared__ __align__(16) unsigned int s_hist[264];
+  __shared__ __align__(16) uint2 s_buf[128];
+  __shared__ unsigned int s_cand[64];
+  __shared__ VbCtl s_ctl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = blockIdx.x;
+  if (r >= R) return;
+  VbCtl *ctl = &s_ctl;
+  const typename Rows::Cursor cur = rows.cursor(r);
+  const int W4 = W >> 2;
+  float x[E];
+  uint32_t vmask = 0u;                                       // bit e: slot e holds data
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int sl = lane * 4 + i;
-        const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
-        c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
-      }
-      bitonic_step_reg32<2, 1>(c, lane);
-      bitonic_step_reg32<4, 2>(c, lane);   bitonic_step_reg32<4, 1>(c, lane);
-      bitonic_step_reg32<8, 4>(c, lane);   bitonic_step_reg32<8, 2>(c, lane);   bitonic_step_reg32<8, 1>(c, lane);
-      bitonic_step_reg32<16, 8>(c, lane);  bitonic_step_reg32<16, 4>(c, lane);  bitonic_step_reg32<16, 2>(c, lane);
-      bitonic_step_reg32<16, 1>(c, lane);
-      bitonic_step_reg32<32, 16>(c, lane); bitonic_step_reg32<32, 8>(c, lane);  bitonic_step_reg32<32, 4>(c, lane);
-      bitonic_step_reg32<32, 2>(c, lane);  bitonic_step_reg32<32, 1>(c, lane);
-      bitonic_step_reg32<64, 32>(c, lane); bitonic_step_reg32<64, 16>(c, lane); bitonic_step_reg32<64, 8>(c, lane);
-      bitonic_step_reg32<64, 4>(c, lane);  bitonic_step_reg32<64, 2>(c, lane);  bitonic_step_reg32<64, 1>(c, lane);
-      bitonic_step_reg32<128, 64>(c, lane); bitonic_step_reg32<128, 32>(c, lane); bitonic_step_reg32<128, 16>(c, lane);
-      bitonic_step_reg32<128, 8>(c, lane);  bitonic_step_reg32<128, 4>(c, lane);  bitonic_step_reg32<128, 2>(c, lane);
-      bitonic_step_reg32<128, 1>(c, lane);
-      // duplicates: position p and p + 1 carry the same key (p < k - 1)
-      const uint32_t nxt0 = __shfl_down_sync(0xffffffffu, c[0], 1);
-      bool dup = false;
+  for (int i = 0; i < NI4; ++i) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i * VB_THREADS + tid < W4) {
+      v = __ldg(reinterpret_cast<const float4 *>(cur.at((i * VB_THREADS + tid) * 4)));
+      vmask |= 0xfu << (4 * i);
+    }
+    x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+  }
+  // ---- row statistics: key range and a NaN / infinity detector ----
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  float nf = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t nx = (i < 3) ? c[i + 1] : nxt0;
-        const bool last = (i == 3) && (lane == 31);
-        dup = dup || (!last && lane * 4 + i + 1 < k && (c[i] >> 7) == (nx >> 7));
-      }
-      if (!__any_sync(0xffffffffu, dup)) {
+  for (int e = 0; e < E; ++e) {
+    if ((vmask >> e) & 1u) {
+      const uint32_t kk = f2key_fast(x[e]);
+      kmin = min(kmin, kk);
+      kmax = max(kmax, kk);
+      nf = fmaf(x[e], 0.f, nf);
+    }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  const bool wbad = __any_sync(0xffffffffu, !(nf == 0.f));
+  if (lane == 0) {
+    ctl->kmin[warp] = kmin;
+    ctl->kmax[warp] = kmax;
+    ctl->bad[warp] = wbad ? 1u : 0u;
+  }
+  if (tid < 128) s_buf[tid] = make_uint2(0u, 0u);
+  if (tid == 0) ctl->cand_n = 0u;
+  __syncthreads();
+  bool bad = false;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int p2 = lane * 4 + i;
-          if (p2 < k) {
-            const uint2 w = buf[127 - (int)(c[i] & 127u)];
-            vrow[p2] = __uint_as_float(w.y);
-            irow[p2] = (int)~w.x;
-          }
+  for (int w = 0; w < 8; ++w) {
+    kmin = min(kmin, ctl->kmin[w]);
+    kmax = max(kmax, ctl->kmax[w]);
+    bad = bad || (ctl->bad[w] != 0u);
+  }
+  const float xmin = key2f(kmin), xmax = key2f(kmax);
+  const float range = xmax - xmin;
+  const bool irregular = bad || !(range > 0.f) || !(range <= 3.0e38f);
+  const uint32_t hist_addr = (uint32_t)__cvta_generic_to_shared(s_hist);
+  const uint32_t dummy = hist_addr + 260u * 4u;
+  int need = k;
+  bool done = false, exact = false;
+  uint32_t tkey = 0u;
+
+  if (!irregular) {
+    // ---- one histogram pass over 256 value bins ----
+    const float scale = 255.f / range;
+    const float off = 8388608.f;
+    if (tid < 66) reinterpret_cast<uint4 *>(s_hist)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const uint32_t hbase = hist_addr - (0x4b000000u << 2);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const uint32_t yb = __float_as_uint(fmaf(x[e] - xmin, scale, off));
+      const uint32_t addr = ((vmask >> e) & 1u) ? (yb << 2) + hbase : dummy;
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    }
+    __syncthreads();
+    if (warp == 0) vb_scan_hist(s_hist, need, lane, ctl);
+    __syncthreads();
+    const int bin = (int)ctl->bin, cntb = (int)ctl->cntb, rem = (int)ctl->rem;
+    if (rem >= 1 && cntb >= rem && cntb <= 32) {
+      const uint32_t ytarget = 0x4b000000u + (uint32_t)bin;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (((vmask >> e) & 1u) && __float_as_uint(fmaf(x[e] - xmin, scale, off)) == ytarget) {
+          const unsigned int pos = atomicAdd(&ctl->cand_n, 1u);
+          if (pos < 64u) s_cand[pos] = __float_as_uint(x[e]);
         }
-        sorted_done = true;
       }
-    }
-    if (!sorted_done) {
-    // composites key | ~index (value bits -> order-preserving key; empty slots stay 0 = below every key; -0 and +0
-    // get the same key so that they order by index)
-    unsigned long long c4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint2 w = buf[lane * 4 + i];
-      const uint32_t kk = (lane * 4 + i < k) ? f2key_fast(__uint_as_float(w.y)) : 0u;
-      c4[i] = ((unsigned long long)kk << 32) | w.x;
-    }
-    bitonic_step_reg<2, 1>(c4, lane);
-    bitonic_step_reg<4, 2>(c4, lane);   bitonic_step_reg<4, 1>(c4, lane);
-    bitonic_step_reg<8, 4>(c4, lane);   bitonic_step_reg<8, 2>(c4, lane);   bitonic_step_reg<8, 1>(c4, lane);
-    bitonic_step_reg<16, 8>(c4, lane);  bitonic_step_reg<16, 4>(c4, lane);  bitonic_step_reg<16, 2>(c4, lane);
-    bitonic_step_reg<16, 1>(c4, lane);
-    bitonic_step_reg<32, 16>(c4, lane); bitonic_step_reg<32, 8>(c4, lane);  bitonic_step_reg<32, 4>(c4, lane);
-    bitonic_step_reg<32, 2>(c4, lane);  bitonic_step_reg<32, 1>(c4, lane);
-    bitonic_step_reg<64, 32>(c4, lane); bitonic_step_reg<64, 16>(c4, lane); bitonic_step_reg<64, 8>(c4, lane);
-    bitonic_step_reg<64, 4>(c4, lane);  bitonic_step_reg<64, 2>(c4, lane);  bitonic_step_reg<64, 1>(c4, lane);
-    bitonic_step_reg<128, 64>(c4, lane); bitonic_step_reg<128, 32>(c4, lane); bitonic_step_reg<128, 16>(c4, lane);
-    bitonic_step_reg<128, 8>(c4, lane);  bitonic_step_reg<128, 4>(c4, lane);  bitonic_step_reg<128, 2>(c4, lane);
-    bitonic_step_reg<128, 1>(c4, lane);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p2 = lane * 4 + i;
-      if (p2 < k) {
-        const int id = (int)~(uint32_t)(c4[i] & 0xffffffffu);
-        vrow[p2] = key2f((uint32_t)(c4[i] >> 32));
-        irow[p2] = id;
+      __syncthreads();
+      if (warp == 0) {
+        const float ci = (lane < cntb) ? __uint_as_float(s_cand[lane]) : 0.f;
+        int gt = 0, eqb = 0, eqt = 0;
+        for (int j = 0; j < cntb; ++j) {
+          const float cj = __shfl_sync(0xffffffffu, ci, j);
+          gt += (cj > ci) ? 1 : 0;
+          eqt += (cj == ci) ? 1 : 0;
+          eqb += (cj == ci && j < lane) ? 1 : 0;
+        }
+        const uint32_t sel = __ballot_sync(0xffffffffu, lane < cntb && gt + eqb == rem - 1);
+        const int src = __ffs(sel) - 1;
+        const float T = __shfl_sync(0xffffffffu, ci, src);
+        const int gt_t = __shfl_sync(0xffffffffu, gt, src);
+        const int eq_t = __shfl_sync(0xffffffffu, eqt, src);
+        if (lane == 0) {
+          ctl->tkey = f2key_fast(T);
+          ctl->need = (unsigned int)(rem - gt_t);
+          ctl->exact = (eq_t == rem - gt_t) ? 1u : 0u;
+        }
       }
+      __syncthreads();
+      tkey = ctl->tkey;
+      need = (int)ctl->need;
+      exact = ctl->exact != 0u;
+      done = true;
     }
+  }
+  if (!done) {
+    // ---- multi-pass radix select on integer keys (256 buckets of the candidates' key range per pass) ----
+    int shift = 32 - __clz((kmax - kmin) | 1u) - 8;
+    if (shift < 0) shift = 0;
+    uint32_t lo = kmin, span_m1 = 0xffffffffu;
+    need = k;
+#pragma unroll 1
+    for (;;) {
+      __syncthreads();
+      if (tid < 66) reinterpret_cast<uint4 *>(s_hist)[tid] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const uint32_t dk = f2key_fast(x[e]) - lo;
+        const bool in = ((vmask >> e) & 1u) && dk <= span_m1;
+        const uint32_t addr = in ? hist_addr + ((dk >> shift) << 2) : dummy;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+      }
+      __syncthreads();
+      if (warp == 0) vb_scan_hist(s_hist, need, lane, ctl);
+      __syncthreads();
+      const int bin = (int)ctl->bin, cntb = (int)ctl->cntb;
+      need = (int)ctl->rem;
+      lo += (uint32_t)bin << shift;
+      if (cntb == need) {
+        exact = true;
+        break;
+      }
+      if (shift == 0) break;
+      span_m1 = (1u << shift) - 1u;
+      shift = (shift > 8) ? shift - 8 : 0;
     }
+    tkey = lo;
+  }
+  // ---- winners: key >= T, or key > T plus the `need` lowest-index elements with key == T ----
+  uint32_t wmask = 0u;
+  if (exact) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (((vmask >> e) & 1u) && f2key_fast(x[e]) >= tkey) wmask |= 1u << e;
   } else {
+    int need_eq = need;
+#pragma unroll 1
+    for (int i = 0; i < NI4; ++i) {
+      uint32_t eqm = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t2 = lane + 32 * i;
-      if (t2 < k) {
-        const uint2 cc = buf[t2];
-        vrow[t2] = __uint_as_float(cc.y);
-        irow[t2] = (int)~cc.x;
+      for (int cc = 0; cc < 4; ++cc) {
+        float xv = 0.f;
+#pragma unroll
+        for (int ii = 0; ii < NI4; ++ii)
+          if (ii == i) xv = x[4 * ii + cc];
+        const bool ok = (vmask >> (4 * i + cc)) & 1u;
+        const uint32_t kk = f2key_fast(xv);
+        if (ok && kk > tkey) wmask |= 1u << (4 * i + cc);
+        if (ok && kk == tkey) eqm |= 1u << cc;
+      }
+      int total;
+      int before = vb_excl_scan(__popc(eqm), total, ctl->wsum, warp, lane);   // index order: thread, then component
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if ((eqm >> cc) & 1u) {
+          if (before < need_eq) wmask |= 1u << (4 * i + cc);
+          ++before;
+        }
+      }
+      need_eq -= min(need_eq, total);
+    }
+  }
+  {
+    int total;
+    int pos = vb_excl_scan(__popc(wmask), total, ctl->wsum, warp, lane);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if ((wmask >> e) & 1u) {
+        const uint32_t id = (uint32_t)(((e >> 2) * VB_THREADS + tid) * 4 + (e & 3));
+        if (pos < 128) s_buf[pos] = make_uint2(~id, __float_as_uint(x[e]));
+        ++pos;
       }
     }
   }
+  __syncthreads();
+  if (warp == 0)
+    emit_winners<SORTED>(s_buf, k, lane, tkey, kmax, vals + (size_t)r * k, idx + (size_t)r * k);
 }
 
 // One 256-thread block per row, any width: three radix passes (11 + 11 + 10 bits) with shared-memory
@@ -1520,6 +1807,18 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
       EDRL_LAUNCHED();
       return 0;
     }
+  }
+  if (uniform && Wmax > 2048 && Wmax <= 8192 && k <= 128 && !legacy && !novec && rows.vec4_ok()) {
+    // wide rows: one 256-thread block per row, the row in registers (4 or 8 float4 per thread)
+    if (Wmax <= 4096) {
+      if (sorted) topk_vecblock_kernel<4, true, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+      else topk_vecblock_kernel<4, false, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+    } else {
+      if (sorted) topk_vecblock_kernel<8, true, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+      else topk_vecblock_kernel<8, false, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+    }
+    EDRL_LAUNCHED();
+    return 0;
   }
   if (Wmax <= 2048 && k <= 128 && !legacy) {
     const bool full = uniform && (Wmax % 32 == 0);

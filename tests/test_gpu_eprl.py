@@ -80,9 +80,9 @@ def test_topk_ties_and_specials(W):
 
 
 @pytest.mark.parametrize("W,k", [(800, 100), (1600, 100), (1024, 128), (2048, 100), (216, 32), (144, 144 // 2), (100, 7),
-                                 (512, 1), (256, 100)])
+                                 (512, 1), (256, 100), (8192, 100), (4096, 64), (2052, 17), (5000, 128)])
 def test_topk_vectorised_select_paths(W, k):
-    """The vectorised warp select (csrc/eprl.cu topk_vec_kernel) and every way out of its fast path: ties at the
+    """The vectorised warp select (csrc/eprl.cu topk_vec_kernel; topk_vecblock_kernel for W > 2048) and every way out of its fast path: ties at the
     threshold, +-0, a crowded threshold bin (> 32 values, or > 4 in one lane), constant rows, NaN / infinities."""
     import edrl_b200
     rng = np.random.default_rng(W * 31 + k)
