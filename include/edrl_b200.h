@@ -57,9 +57,11 @@ int         edrl_abi_version(void);
 const char *edrl_last_error(void);
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 uint64_t    edrl_launch_count(void);
-/* Bind the calling host thread to CUDA device `device` (cudaSetDevice).  The library links its own
- * static CUDA runtime, so a host that selects devices through another runtime instance (PyTorch)
- * calls this before the compute entry points; they all run on the calling thread's current device. */
+/* Name the CUDA device the calling host thread's next compute calls run on.  The library links its own
+ * static CUDA runtime, so a host that selects devices through another runtime instance (PyTorch) calls this
+ * before the compute entry points.  Every entry point that takes a stream binds the thread to that device
+ * for the duration of the call and restores the caller's current device before it returns (the two runtimes
+ * share the primary contexts: a lasting cudaSetDevice would move the caller's later allocations). */
 int         edrl_set_device(int device);
 
 /* ------------------------------------------------------------------------------------------

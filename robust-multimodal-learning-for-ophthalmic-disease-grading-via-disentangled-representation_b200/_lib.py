@@ -129,7 +129,8 @@ def ptr(t):
 
 
 def stream_and_device(t: torch.Tensor):
-    """Current torch stream handle for t's device; binds the library's runtime to that device."""
+    """Current torch stream handle for t's device; names that device to the library (each C-ABI call binds the thread
+    to it for its own duration and restores torch's current device before returning)."""
     dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
     check(load().edrl_set_device(dev))
     return torch.cuda.current_stream(dev).cuda_stream

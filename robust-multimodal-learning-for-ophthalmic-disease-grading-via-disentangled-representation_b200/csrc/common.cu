@@ -9,6 +9,7 @@ namespace edrl {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+thread_local int g_target_device = -1;
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -72,7 +73,7 @@ static int make_tmap_2d(CUtensorMap *out, CUtensorMapDataType dt, const void *ba
 }
 
 int device_sm_count() {
-  static int sms = 0;
+  static int sms = 0;            // (one node carries one GPU model: the first device asked answers for all)
   if (sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -88,7 +89,10 @@ int edrl_abi_version(void) { return EDRL_ABI_VERSION; }
 const char *edrl_last_error(void) { return edrl::g_err; }
 uint64_t edrl_launch_count(void) { return edrl::g_launches.load(std::memory_order_relaxed); }
 int edrl_set_device(int device) {
-  EDRL_CUDA_OK(cudaSetDevice(device));
+  int count = 0;
+  EDRL_CUDA_OK(cudaGetDeviceCount(&count));
+  EDRL_CHECK_ARG(device >= 0 && device < count, "edrl_set_device: device %d outside [0, %d)", device, count);
+  edrl::g_target_device = device;      // bound per call by DeviceGuard; the caller's current device is left alone
   return 0;
 }
 }

@@ -52,6 +52,33 @@ int make_tmap_2d_f16(CUtensorMap *out, const void *base, uint64_t rows, uint64_t
 
 int device_sm_count();
 
+// The device the next C-ABI calls of this thread run on (edrl_set_device); -1 = whatever is current.
+extern thread_local int g_target_device;
+
+// Binds the calling thread to that device for the duration of ONE C-ABI call and restores the caller's current
+// device afterwards: the library's (static) runtime shares the primary contexts with the host framework, so a
+// lasting cudaSetDevice here would silently move the caller's later allocations to another GPU.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  DeviceGuard() {
+    dev = g_target_device;
+    if (dev < 0 || cudaGetDevice(&prev) != cudaSuccess) {
+      prev = dev = -1;
+      return;
+    }
+    if (dev != prev && cudaSetDevice(dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      prev = dev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && dev != prev) (void)cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define EDRL_DEVICE_GUARD() ::edrl::DeviceGuard _edrl_device_guard
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace edrl

@@ -400,8 +400,10 @@ score_bwd_dzpn_kernel(const float *__restrict__ datt, const float *__restrict__ 
 }
 
 // ----------------------------------------------------------------------------- K7 top-k
-// Order-preserving key: larger float <=> larger uint32 (positive NaN sorts first, like torch.topk).
+// Order-preserving key: larger float <=> larger uint32; every NaN, whatever its sign bit, gets the largest key
+// (torch.topk treats NaN as greater than anything).
 __device__ __forceinline__ uint32_t f2key(float x) {
+  if (x != x) return 0xffffffffu;
   const uint32_t u = __float_as_uint(x + 0.f);               // -0 -> +0: the two compare equal, so they must tie
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
@@ -503,7 +505,7 @@ topk_warp_kernel(Rows rows, int R, int k, int KP, float *__restrict__ vals, int 
     if (j < W) {
       int run;
       kv = f2key(__ldg(rows.seg(r, j, run)));
-      if (kv == 0u) kv = 1u;               // keep 0 reserved for padding (only -NaN payload ~0 maps here)
+      if (kv == 0u) kv = 1u;               // keep 0 reserved for padding
     }
     key[e] = kv;
   }
@@ -721,7 +723,7 @@ __device__ __forceinline__ void radix_select_row(const Rows &rows, int r, int k,
   for (int e = 0; e < E; ++e) {
     const int j = e * 32 + lane;
     if (FULL || j < W)
-      key[e] = max(f2key_fast(__ldg(cur.at(j))), 1u);        // 0 stays reserved for padding (only -NaN maps there)
+      key[e] = max(f2key(__ldg(cur.at(j))), 1u);             // 0 stays reserved for padding (NaNs of either sign: top key)
     else
       key[e] = 0u;
   }
@@ -1434,21 +1436,29 @@ topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, i
     }
     x[4 * i + 0] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
   }
-  // ---- row statistics: key range and a NaN / infinity detector ----
-  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  // ---- row statistics: a NaN / infinity detector, then the key range ----
   float nf = 0.f;
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if ((vmask >> e) & 1u) nf = fmaf(x[e], 0.f, nf);
+  const bool wbad = __any_sync(0xffffffffu, !(nf == 0.f));
+  if (wbad) {
+    // NaNs of either sign become the canonical positive NaN: the largest key, as torch.topk orders them
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (x[e] != x[e]) x[e] = __int_as_float(0x7fc00000);
+  }
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     if ((vmask >> e) & 1u) {
       const uint32_t kk = f2key_fast(x[e]);
       kmin = min(kmin, kk);
       kmax = max(kmax, kk);
-      nf = fmaf(x[e], 0.f, nf);
     }
   }
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
-  const bool wbad = __any_sync(0xffffffffu, !(nf == 0.f));
   if (lane == 0) {
     ctl->kmin[warp] = kmin;
     ctl->kmax[warp] = kmax;
@@ -1966,6 +1976,7 @@ extern "C" {
 
 int edrl_token_stats_fwd(const float *z, int B, int T, int F, float *zbar, float *colsum, float *colnorm,
                          void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(z && zbar && colsum && colnorm, "token_stats_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0 && B <= 65535, "token_stats_fwd: bad shape B=%d T=%d F=%d", B, T, F);
   const bool v4 = (F % 4 == 0) && ((((uintptr_t)z | (uintptr_t)zbar | (uintptr_t)colsum | (uintptr_t)colnorm) & 15) == 0);
@@ -1986,6 +1997,7 @@ int edrl_token_stats_fwd(const float *z, int B, int T, int F, float *zbar, float
 
 int edrl_token_stats_bwd(const float *z, const float *colsum, const float *colnorm, const float *dzbar, int B, int T,
                          int F, float *dz, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(z && colsum && colnorm && dzbar && dz, "token_stats_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0, "token_stats_bwd: bad shape");
   const bool v4 = (F % 4 == 0) && (256 % (F / 4) == 0) && B <= 65535 &&
@@ -2006,6 +2018,7 @@ int edrl_token_stats_bwd(const float *z, const float *colsum, const float *colno
 }
 
 int edrl_token_featmean(const float *z, const float *colnorm, int B, int T, int F, float *zmean, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(z && colnorm && zmean, "token_featmean: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && F > 0, "token_featmean: bad shape");
   token_featmean_kernel<<<(B * T + 7) / 8, 256, 0, ST(stream)>>>(z, colnorm, B, T, F, zmean);
@@ -2015,6 +2028,7 @@ int edrl_token_featmean(const float *z, const float *colnorm, int B, int T, int 
 
 int edrl_proxy_normalize_fwd(const float *mu, const float *sigma, const float *eps, int C, int S, int F, float *z_pn,
                              float *pnorm, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(mu && sigma && eps && z_pn && pnorm, "proxy_normalize_fwd: null argument");
   EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_fwd: bad shape");
   dim3 grid((F + 31) / 32, C), block(32, 32);
@@ -2025,6 +2039,7 @@ int edrl_proxy_normalize_fwd(const float *mu, const float *sigma, const float *e
 
 int edrl_proxy_normalize_bwd(const float *mu, const float *sigma, const float *eps, const float *pnorm,
                              const float *dz_pn, int C, int S, int F, float *dmu, float *dsigma, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(mu && sigma && eps && pnorm && dz_pn && dmu && dsigma, "proxy_normalize_bwd: null argument");
   EDRL_CHECK_ARG(C > 0 && S > 0 && F > 0, "proxy_normalize_bwd: bad shape");
   dim3 grid((F + 31) / 32, C), block(32, 32);
@@ -2034,6 +2049,7 @@ int edrl_proxy_normalize_bwd(const float *mu, const float *sigma, const float *e
 }
 
 int edrl_score_fwd(const float *zbar, const float *z_pn, int B, int R, int F, float *att, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(zbar && z_pn && att, "score_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_fwd: bad shape");
   // att[b, r] = sum_f zbar[b, f] z_pn[r, f]
@@ -2045,6 +2061,7 @@ int edrl_score_fwd(const float *zbar, const float *z_pn, int B, int R, int F, fl
 
 int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int B, int R, int F, float *dzbar,
                    float *dz_pn, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(datt && zbar && z_pn, "score_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && R > 0 && F > 0, "score_bwd: bad shape");
   EDRL_CHECK_ARG(B <= 65535, "score_bwd: batch too large");
@@ -2066,6 +2083,7 @@ int edrl_score_bwd(const float *datt, const float *zbar, const float *z_pn, int 
 
 int edrl_topk_rows(const float *x, int R, int W, int ld, int k, int sorted, float *vals, int32_t *idx,
                    void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(x && vals && idx, "topk: null argument");
   EDRL_CHECK_ARG(R > 0 && W > 0 && ld >= W, "topk: bad shape R=%d W=%d ld=%d", R, W, ld);
   EDRL_CHECK_ARG(k >= 1 && k <= W, "selected index k out of range (k=%d, row width %d)", k, W);
@@ -2075,6 +2093,7 @@ int edrl_topk_rows(const float *x, int R, int W, int ld, int k, int sorted, floa
 
 int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S, int k, int sorted, float *pos_val,
                          int32_t *pos_idx, float *neg_val, int32_t *neg_idx, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(att && y && pos_val && pos_idx && neg_val && neg_idx, "select_topk_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && C >= 2 && S > 0, "select_topk_fwd: bad shape B=%d C=%d S=%d", B, C, S);
   EDRL_CHECK_ARG(k >= 1 && k <= S, "selected index k out of range (k=%d, row width %d)", k, S);
@@ -2087,6 +2106,7 @@ int edrl_select_topk_fwd(const float *att, const int64_t *y, int B, int C, int S
 
 int edrl_proxy_loss_fwd(const float *pos_val, const float *neg_val, int B, int k, float *loss, float *rowexp,
                         void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(pos_val && neg_val && loss && rowexp, "proxy_loss_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && k > 0, "proxy_loss_fwd: bad shape");
   proxy_loss_fwd_kernel<<<1, 256, 0, ST(stream)>>>(pos_val, neg_val, B, k, loss, rowexp);
@@ -2096,6 +2116,7 @@ int edrl_proxy_loss_fwd(const float *pos_val, const float *neg_val, int B, int k
 
 int edrl_select_loss_bwd(const float *rowexp, const int32_t *pos_idx, const int32_t *neg_idx, const int64_t *y,
                          const float *grad_out, int B, int C, int S, int k, float *datt, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(rowexp && pos_idx && neg_idx && y && grad_out && datt, "select_loss_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && C >= 2 && S > 0 && k > 0, "select_loss_bwd: bad shape");
   select_loss_bwd_kernel<<<B, 256, 0, ST(stream)>>>(rowexp, pos_idx, neg_idx,
@@ -2110,6 +2131,7 @@ static int vec4_ok(const void *a, const void *b, int D) {
 
 int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T, int D, int k, float *out,
                          void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(features && idx && out, "gather_rows_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && D > 0 && k > 0, "gather_rows_fwd: bad shape");
   const long long rows = (long long)B * k;
@@ -2121,6 +2143,7 @@ int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T
 
 int edrl_gather_rows_bwd(const float *dout, const int32_t *idx, int B, int T, int D, int k, float *dfeatures,
                          void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(dout && idx && dfeatures, "gather_rows_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && T > 0 && D > 0 && k > 0, "gather_rows_bwd: bad shape");
   EDRL_CHECK_ARG((size_t)T * sizeof(int) <= 48 * 1024, "gather_rows_bwd: T = %d too large", T);
@@ -2172,6 +2195,7 @@ size_t edrl_essence_scratch_floats(int B, int T, int F, int C, int S, int k) {
 
 int edrl_essence_train_fwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
                            int F, int C, int S, int k, float *loss, float *saved, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(z && proxies && eps && y && loss && saved, "essence_train_fwd: null argument");
   EDRL_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && F > 0 && C >= 2 && S > 0, "essence_train_fwd: bad shape");
   EDRL_CHECK_ARG(k >= 1 && k <= S, "selected index k out of range (k=%d, row width %d)", k, S);
@@ -2195,6 +2219,7 @@ int edrl_essence_train_fwd(const float *z, const float *proxies, const float *ep
 int edrl_essence_train_bwd(const float *z, const float *proxies, const float *eps, const int64_t *y, int B, int T,
                            int F, int C, int S, int k, const float *saved, const float *grad_out, float *scratch,
                            float *dz, float *dproxies, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(z && proxies && eps && y && saved && grad_out && scratch, "essence_train_bwd: null argument");
   EDRL_CHECK_ARG(B > 0 && B <= 65535 && T > 0 && F > 0 && C >= 2 && S > 0 && k >= 1 && k <= S,
                  "essence_train_bwd: bad shape");

@@ -450,6 +450,7 @@ size_t edrl_mmd_workspace_bytes(int n_s, int n_t, int d, int flags) {
 int edrl_mmd_forward(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                      int flags, int tile_rank, int tile_world, float *loss, float *stats, double *partial,
                      void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(X && Y, "MK_MMD: null input");
   EDRL_CHECK_ARG(tile_world > 1 ? partial != nullptr : (loss && stats), "MK_MMD: null output");
   return forward_impl(MODE_LOSS, X, Y, n_s, n_t, d, kernel_mul, kernel_num, flags, tile_rank, tile_world, loss, stats,
@@ -458,6 +459,7 @@ int edrl_mmd_forward(const float *X, const float *Y, int n_s, int n_t, int d, fl
 
 int edrl_mmd_finalize(const double *partial, int n_s, int n_t, float kernel_mul, int kernel_num, float *loss,
                       float *stats, void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(partial && loss && stats && workspace, "edrl_mmd_finalize: null argument");
   EDRL_CHECK_ARG(workspace_bytes >= 256, "edrl_mmd_finalize: workspace too small");
   mmd_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -468,6 +470,7 @@ int edrl_mmd_finalize(const double *partial, int n_s, int n_t, float kernel_mul,
 
 int edrl_mmd_kernel_matrix(const float *X, const float *Y, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                            int flags, float *K, void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(X && Y && K, "gaussian_kernel: null argument");
   const int mode = (flags & 0x100) ? MODE_GRAM : MODE_KMAT;   // 0x100: debug, raw centred Gram
   return forward_impl(mode, X, Y, n_s, n_t, d, kernel_mul, kernel_num, flags & 0xff, 0, 1, nullptr, nullptr, nullptr,
@@ -477,6 +480,7 @@ int edrl_mmd_kernel_matrix(const float *X, const float *Y, int n_s, int n_t, int
 int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num, int flags, const float *stats,
                       const float *grad_out, int row_begin, int row_count, float *dZ, void *workspace,
                       size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   Layout L = make_layout(n_s, n_t, d, flags);
   if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
   EDRL_CHECK_ARG(stats && grad_out && dZ, "MK_MMD backward: null argument");
@@ -551,6 +555,7 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
                           int flags, int row_begin, int row_count, int row_begin2, int row_count2, int finalize,
                           float *loss, float *stats, double *partial, float *U, void *workspace,
                           size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(X && Y && U, "MK_MMD forward_grad: null argument");
   EDRL_CHECK_ARG((flags & EDRL_MMD_3XTF32) == 0, "MK_MMD forward_grad: the fused pass is TF32 / TF32H only");
   Layout L = make_layout(n_s, n_t, d, flags);
@@ -627,6 +632,7 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
 int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, const float *grad_out,
                         const float *U, int row_begin, int row_count, int row_begin2, int row_count2, float *dZ,
                         void *workspace, size_t workspace_bytes, void *stream) {
+  EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(stats && grad_out && U && dZ && workspace, "MK_MMD apply_grad: null argument");
   Layout L = make_layout(n_s, n_t, d, flags);
   EDRL_CHECK_ARG(workspace_bytes >= L.total, "MK_MMD apply_grad: workspace too small");

@@ -272,7 +272,7 @@ class EPRL(nn.Module):
     """
 
     def __init__(self, x_dim, z_dim=256, beta=1e-2, sample_num=50, topk=1, num_classes=3, seed=1, batch_size=16,
-                 noise="reference", validate_labels=True):
+                 noise="reference", validate_labels="lazy"):
         super().__init__()
         self.beta = beta
         self.sample_num = sample_num
@@ -296,7 +296,12 @@ class EPRL(nn.Module):
         if noise not in ("reference", "device"):
             raise ValueError("noise must be 'reference' or 'device'")
         self.noise = noise
+        if validate_labels not in (True, False, "lazy"):
+            raise ValueError("validate_labels must be True, False or 'lazy'")
         self.validate_labels = validate_labels
+        self._verdict_host = None
+        self._verdict_event = None
+        self._verdict_batch = 0
         self.self_topk = SELF_TOPK
         self._eval_gen = None
 
@@ -336,15 +341,52 @@ class EPRL(nn.Module):
     # ---- label handling ------------------------------------------------------------------------
     def _proxy_indices(self, labels):
         """proxies_dict lookup (code/fusion_net.py:101,186,227): labels outside {0,1} raise KeyError.
-        One range check on the device instead of one host sync per label."""
+
+        ``validate_labels="lazy"`` (default): the range check runs on the device, its verdict goes to pinned host memory
+        with an asynchronous copy and is looked at by the NEXT call (or by ``check_labels()``), so the training step never
+        waits for the GPU -- the reference pays one device-to-host sync per label here.  ``True``: checked at once (one
+        sync per call), the reference's timing of the KeyError.  ``False``: not checked (the kernels clamp)."""
         labels = labels.to(self.proxies.device).long().reshape(-1)
-        if self.validate_labels and labels.numel():
+        mode = self.validate_labels
+        if mode and labels.numel():
             lo, hi = torch.aminmax(labels)
-            lo, hi = int(lo), int(hi)
-            for bad in (lo, hi):
-                if str(bad) not in self.proxies_dict:
-                    raise KeyError(str(bad))
+            if mode == "lazy":
+                self.check_labels()
+                self._post_verdict(torch.stack([((lo < 0) | (hi > 1)).long(), torch.where(lo < 0, lo, hi),
+                                                torch.zeros_like(lo)]))
+            else:
+                lo, hi = torch.stack([lo, hi]).tolist()           # one sync for both
+                for bad in (lo, hi):
+                    if str(bad) not in self.proxies_dict:
+                        raise KeyError(str(bad))
         return labels
+
+    def _post_verdict(self, verdict):
+        """verdict: int64[3] on the device = (label out of range?, the offending label, eval: unbroadcastable count or 0)"""
+        if self._verdict_host is None:
+            self._verdict_host = torch.zeros(3, dtype=torch.int64).pin_memory()
+        self._verdict_host.copy_(verdict, non_blocking=True)
+        self._verdict_event = torch.cuda.Event()
+        self._verdict_event.record(torch.cuda.current_stream(verdict.device))
+
+    def check_labels(self, wait=False):
+        """Raise what the lazy checks of an earlier forward found (KeyError for a label outside proxies_dict,
+        IndexError for the eval branch's unbroadcastable pseudo-label count).  ``wait=True`` blocks until that forward has
+        finished on the device; otherwise a verdict that is still in flight is left for the next call."""
+        ev = self._verdict_event
+        if ev is None:
+            return
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._verdict_event = None
+        bad, label, count = self._verdict_host.tolist()
+        if bad:
+            raise KeyError(str(label))
+        if count:
+            raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
+                             f"[{self._verdict_batch}], [{count}]")
 
     # ---- forward --------------------------------------------------------------------------------
     def forward(self, x, y=None):
@@ -365,21 +407,38 @@ class EPRL(nn.Module):
             combined = self.alpha * pseudo_att + (1 - self.alpha) * pseudo_feat
             confidence, labels = torch.max(combined, dim=1)
             mask = confidence > threshold
-            if mask.sum().item() == 0:
-                mask[confidence.argmax()] = True
-            filtered = labels[mask]
-            proxy_indices = self._proxy_indices(filtered)
-            if proxy_indices.numel() not in (1, B):
-                # the reference's mask[arange(B), proxy_indices] broadcast fails here (:191)
-                raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
-                                 f"[{B}], [{proxy_indices.numel()}]")
-            row_labels = proxy_indices.expand(B).contiguous()
+            if self.validate_labels == "lazy":
+                # the reference's `.item()` (:181), boolean indexing (:184) and per-label Python loop (:186) without a
+                # device-to-host sync: no confident sample -> the most confident one; the surviving pseudo-labels must
+                # number 1 (broadcast to every row) or B (:191), anything else is reported by the next call
+                self.check_labels()
+                none = ~mask.any()
+                mask = mask | (none & F.one_hot(confidence.argmax(), B).bool())
+                count = mask.sum()
+                first = labels[mask.to(torch.uint8).argmax()]
+                row_labels = torch.where(count == B, labels, first.expand(B)).contiguous()
+                sel = torch.where(mask, labels, first.expand(B))
+                lo, hi = torch.aminmax(sel)
+                self._verdict_batch = B
+                self._post_verdict(torch.stack([((lo < 0) | (hi > 1)).long(), torch.where(lo < 0, lo, hi),
+                                                torch.where((count == 1) | (count == B), torch.zeros_like(count), count)]))
+            else:
+                if mask.sum().item() == 0:
+                    mask[confidence.argmax()] = True
+                filtered = labels[mask]
+                proxy_indices = self._proxy_indices(filtered)
+                if proxy_indices.numel() not in (1, B):
+                    # the reference's mask[arange(B), proxy_indices] broadcast fails here (:191)
+                    raise IndexError(f"shape mismatch: indexing tensors could not be broadcast together with shapes "
+                                     f"[{B}], [{proxy_indices.numel()}]")
+                row_labels = proxy_indices.expand(B).contiguous()
             proxy_loss, _, _ = essence_select_loss(att, row_labels, self.self_topk, sorted=False)
             entropy_loss = self.entropy_regularization(combined)
             return mu_proxy.repeat(B, 1, 1), sigma_proxy.repeat(B, 1, 1), proxy_loss, z, entropy_loss
 
-        if B != self.batch_size and self.batch_size != 1:
-            # expand(self.batch_size, ...) against a [B,1,T,F] operand (code/fusion_net.py:221-223)
+        if B != self.batch_size and self.batch_size != 1 and B != 1:
+            # expand(self.batch_size, ...) against a [B,1,T,F] operand (code/fusion_net.py:221-223); B == 1 broadcasts
+            # there (batch_size identical rows, the label index broadcasts at :231): the loss equals the single row's
             raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({self.batch_size}) "
                                "at non-singleton dimension 0")
         if y is None:

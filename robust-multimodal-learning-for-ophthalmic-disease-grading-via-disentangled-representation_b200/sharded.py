@@ -105,8 +105,12 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
                                                  None, partial.data_ptr(), u.data_ptr(), ws.ptr, ws.nbytes, stream))
             ctx.U = u
         else:
+            # (a 1-rank group: the C entry point finalises by itself and wants the outputs; edrl_mmd_finalize below
+            #  rewrites the same values from the partial sums)
+            one = world == 1
             _lib.check(lib.edrl_mmd_forward(x_all.data_ptr(), y_all.data_ptr(), plan.n_s, plan.n_t, d,
-                                            float(kernel_mul), int(kernel_num), flags, rank, world, None, None,
+                                            float(kernel_mul), int(kernel_num), flags, rank, world,
+                                            loss.data_ptr() if one else None, stats.data_ptr() if one else None,
                                             partial.data_ptr(), ws.ptr, ws.nbytes, stream))
         reduce_partials(partial, group)
         _lib.check(lib.edrl_mmd_finalize(partial.data_ptr(), plan.n_s, plan.n_t, float(kernel_mul), int(kernel_num),

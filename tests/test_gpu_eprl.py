@@ -106,7 +106,8 @@ def test_topk_vectorised_select_paths(W, k):
     rows.append(np.arange(W, dtype=np.float64))                                   # ascending
     rows.append(-np.arange(W, dtype=np.float64))                                  # descending
     rows.append(rng.standard_normal(W) * 1e-30)                                   # tiny range
-    x = np.stack(rows).astype(np.float32)
+    x = np.ascontiguousarray(np.stack(rows).astype(np.float32))
+    x.view(np.uint32)[5, W // 3] = 0xffc00000     # a second NaN, sign bit set (what 0 * inf gives on x86): as great as any NaN
     for srt in (True, False):
         v, i = edrl_b200.topk_rows(dev(x), k, sorted=srt)
         v, i = v.cpu().numpy(), i.cpu().numpy()
@@ -236,10 +237,28 @@ def test_module_train_contract_and_errors():
     assert mu.shape == (B, 2, 32) and sigma.shape == (B, 2, 32) and z.shape == (B, T, 32) and loss.dim() == 0
     loss.backward()
     assert x.grad is not None and torch.isfinite(x.grad).all() and model.proxies.grad.abs().sum() > 0
+    # proxies_dict has only "0" and "1".  Default: checked on the device, reported without a sync by the next call or by
+    # check_labels(); validate_labels=True raises at once, like the reference's per-label Python loop
+    model(x, torch.tensor([0, 1, 2, 0]).cuda())
+    with pytest.raises(KeyError, match="2"):
+        model.check_labels(wait=True)
+    model(x, y)
+    model.check_labels(wait=True)                                 # a clean call leaves nothing behind
+    model(x, torch.tensor([0, -1, 1, 0]).cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(KeyError, match="-1"):
+        model(x, y)
+    model.validate_labels = True
     with pytest.raises(KeyError):
-        model(x, torch.tensor([0, 1, 2, 0]).cuda())               # proxies_dict has only "0" and "1"
+        model(x, torch.tensor([0, 1, 2, 0]).cuda())
     with pytest.raises(RuntimeError):
         model(x[:3], y[:3])                                       # B != batch_size
+    # B == 1 broadcasts against batch_size in the reference (expand at :221, label index at :231): the single row's loss
+    one = edrl_b200.EPRL(xd, z_dim=32, sample_num=800, num_classes=2, batch_size=1).cuda().train()
+    one.load_state_dict(model.state_dict())
+    torch.manual_seed(3); l_b = model(x[:1], y[:1])[2]            # (same seed: same dropout mask, same proxy noise)
+    torch.manual_seed(3); l_1 = one(x[:1], y[:1])[2]
+    assert torch.equal(l_b, l_1)
     with pytest.raises(RuntimeError):
         model.cpu()(x.cpu(), y.cpu())                             # no CPU fallback
 

@@ -235,6 +235,112 @@ def test_full_size_properties(mode):
     assert np.isclose(lv, l3, rtol=1e-3)
 
 
+# ---------------------------------------------------------------- parity AT the quoted sizes (BASELINE configs[1], [3])
+def _record(name, payload):
+    """Measured errors of the full-size parity tests, for DESIGN.md (gpurun_out/ travels back from the GPU box)."""
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "parity_full_size.json")
+        try:
+            with open(path) as f:
+                data = json.load(f)
+        except Exception:
+            data = {}
+        data[name] = payload
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1)
+
+
+@pytest.fixture(scope="module")
+def reference_ops_8192():
+    """The reference's own op sequence (oracle/cpu_port.mk_mmd_fwd_bwd: code/MMD.py:16-72 + autograd, the n x n
+    matrices materialised) run on the GPU at N = 8192 per side, d = 512 -- in fp64 (the truth) and in fp32 (what the
+    reference computes).  bench.py's inputs (seed 1013)."""
+    from oracle import cpu_port
+    N, d = 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(1013)
+    x = torch.randn(N, d, device="cuda", generator=g)
+    y = torch.randn(N, d, device="cuda", generator=g) * 1.25 + 0.1
+    l64, dx64, dy64 = cpu_port.mk_mmd_fwd_bwd(x.double(), y.double())
+    torch.cuda.empty_cache()
+    l32, dx32, dy32 = cpu_port.mk_mmd_fwd_bwd(x, y)
+    torch.cuda.empty_cache()
+    return x, y, (l64.item(), dx64, dy64), (l32.item(), dx32, dy32)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
+def test_full_size_vs_reference_ops(reference_ops_8192, mode):
+    """N = 8192 per side, d = 512 (the headline workload): loss and the FULL gradients of every precision mode against
+    the reference op sequence evaluated in fp64 on the same GPU, at the tolerances of SURVEY.md 8c; and against the
+    reference's fp32 evaluation at the reference's own error level."""
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    x, y, (l64, dx64, dy64), (l32, dx32, dy32) = reference_ops_8192
+    xt = x.clone().requires_grad_(True)
+    yt = y.clone().requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, precision=name)
+    loss.backward()
+    gmax = max(dx64.abs().max().item(), dy64.abs().max().item())
+    lerr = abs(loss.item() - l64) / abs(l64)
+    gerr = max((xt.grad.double() - dx64).abs().max().item(), (yt.grad.double() - dy64).abs().max().item()) / gmax
+    ref_lerr = abs(l32 - l64) / abs(l64)
+    ref_gerr = max((dx32.double() - dx64).abs().max().item(), (dy32.double() - dy64).abs().max().item()) / gmax
+    _record(f"N8192_d512_{name}", {"loss": loss.item(), "loss_fp64_reference_ops": l64, "loss_rel_err": lerr,
+                                   "grad_max_err_over_gmax": gerr, "reference_fp32_loss_rel_err": ref_lerr,
+                                   "reference_fp32_grad_err_over_gmax": ref_gerr, "tolerance": [ltol, gtol]})
+    assert lerr <= ltol, (loss.item(), l64)
+    assert gerr <= gtol, gerr
+    # against the reference's own fp32 numbers: both sit within their error of the fp64 truth
+    assert abs(loss.item() - l32) <= (ltol + 2e-4) * abs(l32)
+    assert max((xt.grad - dx32).abs().max().item(), (yt.grad - dy32).abs().max().item()) <= (gtol + 2e-4) * gmax
+
+
+@pytest.fixture(scope="module")
+def blockwise_65536():
+    """fp64 row-blocked restatement of the reference (oracle/blockwise.py) at N = 65536 per side, d = 1024 (BASELINE
+    configs[3], rank 0's generator seeds of bench.py: the whole problem on one GPU): loss, sigma_0 and the gradient rows
+    of 256 sampled rows (both ends of each set, the panel boundaries, random ones)."""
+    from oracle import blockwise
+    N, d = 65536, 1024
+    g = torch.Generator(device="cuda").manual_seed(2000)
+    x = torch.randn(N, d, device="cuda", generator=g)
+    y = torch.randn(N, d, device="cuda", generator=g) * 1.25 + 0.1
+    gr = torch.Generator().manual_seed(5)
+    rows = torch.cat([torch.tensor([0, 1, 127, 128, N - 1, N, N + 1, 2 * N - 1, N + 255, N + 256]),
+                      torch.randint(0, 2 * N, (246,), generator=gr)]).unique()
+    loss, m, s0, grad = blockwise.mk_mmd_blockwise(x, y, rows=rows.cuda(), block=2048)
+    torch.cuda.empty_cache()
+    return x, y, rows.cuda(), loss.item(), s0.item(), grad
+
+
+@pytest.mark.parametrize("mode", [MODES[1], MODES[3]], ids=lambda m: m[0])
+def test_sharded_size_sampled_rows_vs_blockwise_oracle(blockwise_65536, mode):
+    """N = 65536 per side, d = 1024 on ONE GPU (the quad sweep, the kernel behind every configs[3] number): loss,
+    bandwidth and sampled gradient rows against the fp64 row-blocked oracle."""
+    import edrl_b200
+    name, flag, ltol, gtol = mode
+    x, y, rows, l64, s0, g64 = blockwise_65536
+    N = x.shape[0]
+    xt = x.clone().requires_grad_(True)
+    yt = y.clone().requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, precision=name)
+    loss.backward()
+    gz = torch.cat([xt.grad, yt.grad])[rows].double()
+    gmax = g64.abs().max().item()
+    lerr = abs(loss.item() - l64) / abs(l64)
+    gerr = (gz - g64).abs().max().item() / gmax
+    _, st = edrl_b200.mk_mmd_with_stats(x, y, precision=name)
+    _record(f"N65536_d1024_{name}", {"loss": loss.item(), "loss_fp64_blockwise": l64, "loss_rel_err": lerr,
+                                     "sampled_rows": int(rows.numel()), "grad_max_err_over_gmax": gerr,
+                                     "sigma0": st[1].item(), "sigma0_fp64": s0, "tolerance": [ltol, gtol]})
+    assert lerr <= ltol, (loss.item(), l64)
+    assert gerr <= gtol, gerr
+    assert np.isclose(st[1].item(), s0, rtol=1e-5)
+    del xt, yt
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("mode", MODES, ids=lambda m: m[0])
 def test_midsize_vs_oracle(mode):
     """N=2048/side, d=512 -- the largest size the fp64 numpy oracle finishes in seconds."""
