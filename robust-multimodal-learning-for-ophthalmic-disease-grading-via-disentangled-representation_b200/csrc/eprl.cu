@@ -1013,6 +1013,8 @@ __device__ __forceinline__ void emit_winners(uint2 *buf, int k, int lane, uint32
   }
 }
 
+#include "topk_sift.cuh"
+
 // ----------------------------------------------------------------------------- K7b vectorised warp select
 // One warp per row, uniform row width W (a multiple of 4, rows 16-byte aligned), k <= 128.  The select is bound by
 // instruction issue and the integer pipe, not by HBM, so it is built around the instruction count:
@@ -1411,8 +1413,8 @@ __device__ __forceinline__ void vb_scan_hist(const unsigned int *hist, int need,
 }
 
 template <int NI4, bool SORTED, class Rows>
-__global__ void __launch_bounds__(VB_THREADS, 4)
-topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx) {
+__device__ __forceinline__ void vecblock_select_row(const Rows &rows, int r, int W, int k, float *__restrict__ vals,
+                                                    int *__restrict__ idx) {
   constexpr int E = NI4 * 4;
   static_assert(E <= 32, "one 32-bit win mask per thread");
   __shared__ __align__(16) unsigned int s_hist[264];
@@ -1420,8 +1422,6 @@ topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, i
   __shared__ unsigned int s_cand[64];
   __shared__ VbCtl s_ctl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r = blockIdx.x;
-  if (r >= R) return;
   VbCtl *ctl = &s_ctl;
   const typename Rows::Cursor cur = rows.cursor(r);
   const int W4 = W >> 2;
@@ -1622,6 +1622,23 @@ topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, i
     emit_winners<SORTED>(s_buf, k, lane, tkey, kmax, vals + (size_t)r * k, idx + (size_t)r * k);
 }
 
+// marked = 0: block b selects row b.  marked = 1: the blocks walk all rows and redo those the streaming sift kernel
+// marked with idx[r k] = -1 (rows it could not finish on its fast path).
+template <int NI4, bool SORTED, class Rows>
+__global__ void __launch_bounds__(VB_THREADS, 4)
+topk_vecblock_kernel(Rows rows, int R, int W, int k, float *__restrict__ vals, int *__restrict__ idx, int marked) {
+  if (!marked) {
+    if ((int)blockIdx.x < R) vecblock_select_row<NI4, SORTED, Rows>(rows, blockIdx.x, W, k, vals, idx);
+    return;
+  }
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    if (idx[(size_t)r * k] == -1) {                          // (block-uniform)
+      __syncthreads();                                       // the previous row's shared state is done with
+      vecblock_select_row<NI4, SORTED, Rows>(rows, r, W, k, vals, idx);
+    }
+  }
+}
+
 // One 256-thread block per row, any width: three radix passes (11 + 11 + 10 bits) with shared-memory
 // histograms; pass 1 streams the row from global memory, the candidates of the winning bucket are
 // compacted to shared memory for the later passes (falls back to re-streaming if they do not fit).
@@ -1791,6 +1808,33 @@ static void launch_radix(const Rows &rows, int R, int k, bool sorted, bool full,
   }
 }
 
+// Sampling plan of the sift select for rows of width W, k winners, a sample of m elements and a survivors' list of `cap`
+// entries.  The count of row elements above the sample's q-quantile scatters around q W with
+// sigma = W sqrt(q (1 - q) / m): aim the pivot at mu = k + z sigma survivors (z = 3.3: a row in a thousand falls short and
+// takes the slow path) and require that mu + z sigma, plus the pivot's own histogram bin, still fits the list.
+struct SiftPlan {
+  bool ok;
+  int jtarget;
+};
+static SiftPlan sift_plan(int W, int k, int m_samples, int cap) {
+  const double m = (double)m_samples, z = 3.3;
+  double mu = k, sigma = 0.0;
+  for (int it = 0; it < 30; ++it) {
+    const double q = mu / W;
+    if (q >= 0.6) return SiftPlan{false, 0};
+    sigma = W * sqrt(q * (1.0 - q) / m);
+    mu = k + z * sigma;
+  }
+  const double q = mu / W;
+  const double upper = mu + z * sigma + 0.15 * mu;           // (a 64-bin histogram of a bell-shaped row: <= ~0.15 mu per bin)
+  SiftPlan p;
+  p.ok = upper <= cap && q < 0.5;
+  p.jtarget = (int)ceil(q * m);
+  if (p.jtarget < 1) p.jtarget = 1;
+  if (p.jtarget > (int)m) p.ok = false;
+  return p;
+}
+
 // Wmax: widest row; uniform: every row has exactly Wmax elements
 template <class Rows>
 static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, int *idx, cudaStream_t st,
@@ -1799,6 +1843,42 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   EDRL_CHECK_ARG(KP <= 1024, "topk: k = %d is larger than the supported 1024", k);
   static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
   static const bool novec = (getenv("EDRL_TOPK_VEC") != nullptr && atoi(getenv("EDRL_TOPK_VEC")) == 0);
+  static const bool nosift = (getenv("EDRL_TOPK_SIFT") != nullptr && atoi(getenv("EDRL_TOPK_SIFT")) == 0);
+  static const int sift_g = getenv("EDRL_TOPK_SIFT_G") ? atoi(getenv("EDRL_TOPK_SIFT_G")) : 0;   // A/B: 16 or 32 only
+  if (uniform && Wmax >= 128 && Wmax <= 2048 && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
+    // sift select (topk_sift.cuh): sample pivot -> survivors -> exact select, when the sampling plan fits the list;
+    // a half-warp per row up to 1024 elements, a warp per row above
+    const int W4 = Wmax >> 2;
+    bool done = false;
+#define EDRL_SIFT_CASE(G_, FI_, P_, SSTR_, SL_)                                                                      \
+  if (!done && (sift_g == 0 || sift_g == G_) && W4 / G_ == FI_ && ((W4 % G_) != 0) == P_) {                          \
+    const SiftPlan sp = sift_plan(Wmax, k, G_ * ((FI_ * 4 + SSTR_ - 1) / SSTR_), G_ * SL_);                         \
+    if (sp.ok) {                                                                                                      \
+      const int rpb = 4 * (32 / G_);                                                                                  \
+      const int grid = (R + rpb - 1) / rpb;                                                                           \
+      if (sorted)                                                                                                     \
+        topk_sift_kernel<G_, FI_, P_, SSTR_, SL_, true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+      else                                                                                                            \
+        topk_sift_kernel<G_, FI_, P_, SSTR_, SL_, false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+      done = true;                                                                                                    \
+    }                                                                                                                 \
+  }
+    EDRL_SIFT_CASE(16, 2, true, 1, 8)       // W = 144 (fundus token rows)
+    EDRL_SIFT_CASE(16, 3, true, 1, 8)       // W = 216 (OCT token rows)
+    EDRL_SIFT_CASE(16, 4, false, 1, 16)     // W = 256
+    EDRL_SIFT_CASE(16, 8, false, 2, 16)     // W = 512
+    EDRL_SIFT_CASE(16, 12, true, 2, 16)     // W = 800 (the reference's S)
+    EDRL_SIFT_CASE(16, 16, false, 3, 16)    // W = 1024
+    EDRL_SIFT_CASE(32, 6, true, 2, 8)       // W = 800, a warp per row (A/B: EDRL_TOPK_SIFT_G=32)
+    EDRL_SIFT_CASE(32, 8, false, 2, 16)     // W = 1024, large k
+    EDRL_SIFT_CASE(32, 12, true, 3, 16)     // W = 1600 (C = 3 negatives)
+    EDRL_SIFT_CASE(32, 16, false, 4, 16)    // W = 2048
+#undef EDRL_SIFT_CASE
+    if (done) {
+      EDRL_LAUNCHED();
+      return 0;
+    }
+  }
   if (uniform && Wmax <= 2048 && k <= 128 && !legacy && !novec && rows.vec4_ok()) {
     // vectorised warp select for the common uniform widths (W / 4 = 32 FI + partial lanes)
     const int W4 = Wmax >> 2, fi = W4 >> 5;
@@ -1819,13 +1899,29 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
     }
   }
   if (uniform && Wmax > 2048 && Wmax <= 8192 && k <= 128 && !legacy && !novec && rows.vec4_ok()) {
-    // wide rows: one 256-thread block per row, the row in registers (4 or 8 float4 per thread)
+    // wide rows.  Streaming sift select, one warp per row, when the sampling plan fits (1024 sample elements, 512
+    // list entries); the rows it marks -- or, without it, all rows -- go to one 256-thread block per row with the row
+    // in registers (4 or 8 float4 per thread)
+    int marked = 0;
+    if (!nosift) {
+      const SiftPlan sp = sift_plan(Wmax, k, 1024, 512);
+      if (sp.ok) {
+        const int grid = (R + 3) / 4;
+        if (sorted) topk_sift_stream_kernel<true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx);
+        else topk_sift_stream_kernel<false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx);
+        EDRL_LAUNCHED();
+        marked = 1;
+      }
+    }
+    int sms = device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int grid = marked ? (R < 4 * sms ? R : 4 * sms) : R;
     if (Wmax <= 4096) {
-      if (sorted) topk_vecblock_kernel<4, true, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
-      else topk_vecblock_kernel<4, false, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+      if (sorted) topk_vecblock_kernel<4, true, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
+      else topk_vecblock_kernel<4, false, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
     } else {
-      if (sorted) topk_vecblock_kernel<8, true, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
-      else topk_vecblock_kernel<8, false, Rows><<<R, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx);
+      if (sorted) topk_vecblock_kernel<8, true, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
+      else topk_vecblock_kernel<8, false, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
     }
     EDRL_LAUNCHED();
     return 0;

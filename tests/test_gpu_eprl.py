@@ -123,6 +123,48 @@ def test_topk_vectorised_select_paths(W, k):
                 np.testing.assert_array_equal(v[rr], xr[i[rr]], err_msg=f"row {rr}")
 
 
+@pytest.mark.parametrize("W,k", [(800, 100), (1600, 100), (512, 64), (1024, 128), (1024, 100), (216, 32), (144, 32), (256, 32),
+                                 (2048, 100), (8192, 100), (4096, 50), (2052, 100), (800, 1), (800, 128)])
+@pytest.mark.parametrize("dist", ["normal", "uniform", "exp", "cauchy", "lognormal", "int", "two_values", "sorted", "shifted"])
+def test_sift_select_against_stable_sort(W, k, dist):
+    """The sift select (csrc/topk_sift.cuh: sample pivot -> survivors -> exact select; half-warp / warp / streaming
+    variants by row width) over thousands of rows of distributions that do and do not look like a sample of themselves:
+    values and indices bit-exact against a stable descending sort (ties: lowest index first), sorted and unsorted."""
+    import edrl_b200
+    R = 1024 if W >= 4096 else 4096
+    g = torch.Generator(device="cuda").manual_seed(W * 131 + k)
+    if dist == "normal":
+        x = torch.randn(R, W, device="cuda", generator=g)
+    elif dist == "uniform":
+        x = torch.rand(R, W, device="cuda", generator=g) - 0.5
+    elif dist == "exp":
+        x = -torch.log(torch.rand(R, W, device="cuda", generator=g).clamp_min(1e-30))
+    elif dist == "cauchy":
+        x = torch.tan(3.14159 * (torch.rand(R, W, device="cuda", generator=g) - 0.5))
+    elif dist == "lognormal":
+        x = torch.exp(3.0 * torch.randn(R, W, device="cuda", generator=g))
+    elif dist == "int":
+        x = torch.randint(0, 50, (R, W), device="cuda", generator=g).float()
+    elif dist == "two_values":
+        x = (torch.rand(R, W, device="cuda", generator=g) < 0.1).float() * 3.0 - 1.0
+    elif dist == "sorted":
+        x = torch.randn(R, W, device="cuda", generator=g).sort(dim=1).values
+    else:                                                      # a large offset: narrow relative range
+        x = 1.0e4 + 1.0e-2 * torch.randn(R, W, device="cuda", generator=g)
+    sv, si = torch.sort(x, dim=1, descending=True, stable=True)
+    ev, ei = sv[:, :k], si[:, :k]
+    v, i = edrl_b200.topk_rows(x, k, sorted=True)
+    assert torch.equal(v, ev), dist
+    assert torch.equal(i.long(), ei), dist
+    v, i = edrl_b200.topk_rows(x, k, sorted=False)
+    assert torch.equal(i.long().sort(dim=1).values, ei.sort(dim=1).values), dist
+    assert torch.equal(v, torch.gather(x, 1, i.long())), dist
+    # an odd number of rows (an idle half-warp in the last warp) and a strided view
+    xo = x[: R - 3]
+    v, i = edrl_b200.topk_rows(xo, k, sorted=True)
+    assert torch.equal(v, ev[: R - 3]) and torch.equal(i.long(), ei[: R - 3]), dist
+
+
 # ---------------------------------------------------------------- label-addressed select + loss
 @pytest.mark.parametrize("B,C,S,k", [(4, 2, 800, 100), (64, 2, 800, 100), (5, 3, 300, 100), (2, 4, 1000, 100)])
 def test_select_topk_matches_split_plus_topk(B, C, S, k):
