@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A *step* is one MK_MMD forward + backward over one synthetic batch.
+A *step* is one MK_MMD forward + backward over one synthetic batch (Part A of the path; Part B -- the Essence-Point
+select -- is HBM-bound and is measured in the same run on the scaled sweep of SURVEY.md 8d: `roofline.part_b_select`).
   N = 1 : BASELINE configs[1] at its largest size: N = 8192 samples per side, d = 512, fp32 inputs.
   N > 1 : BASELINE configs[3]: N = 65536 per side, d = 1024, row-block sharded over the ranks
-          (NCCL all-gather of the feature rows + all-reduce of two partial sums); fixed total work.
+          (NCCL all-gather of the feature rows + all-reduce of two partial sums); fixed total work.  The N = 1 line also
+          carries `scale_anchor`: the same configs[3] workload on one GPU through the same public API.
 `value` = samples per side / step time, inputs resident in HBM, timed with CUDA events per step
 (L2 flushed between steps, untimed), max over ranks.  `e2e` = the same step through the public API
 from pinned HOST buffers (H2D of X and Y, D2H of the loss and both gradients inside the timed region).
-`roofline` = the dominant kernel (the tile-recomputing backward) alone, algorithmic FLOPs / its duration.
-`cpu_baseline` / `--impl reference` = the reference algorithm's CPU port (oracle/cpu_port.py; the
-reference itself is PyTorch-on-CPU code that cannot travel to the GPU box) on a bounded row-block
-sample of the same problem, all host threads.
+`roofline` = the dominant kernel (the fused forward+gradient Gram sweep) alone, algorithmic FLOPs / its duration
+(`roofline.part_a` repeats it; `roofline.part_b_select` is the select kernel against measured HBM bandwidth).
+`cpu_baseline` / `--impl reference` = the reference's OWN MMD.py (the verbatim copy `oracle/build_ref.py` makes under
+oracle/_ref/, kind "reference"; the torch-CPU port oracle/cpu_port.py when that copy is absent, kind "port") on the
+box's host cores: whole steps of configs[1] for as many of --steps as a time budget allows (`steps_measured`); a
+row-block sample, labelled `extrapolated`, for configs[3], which no single device can run (773 GB of activations).
 """
 from __future__ import annotations
 
@@ -194,65 +198,89 @@ def timed_steps(step_fn, steps, warmup, flush, world):
     return total
 
 
-# ----------------------------------------------------------------------------------------- CPU arm
-def cpu_port_sample(N, d, seed, budget_s=12.0):
-    """Bounded sample of the workload on the host cores: rows [0, m) of the 2N x 2N problem, fwd+bwd.
-    Returns (samples/s extrapolated to the full step, cores, description)."""
-    from oracle import cpu_port                      # baseline leg only: never on the product path
+def config_of(wl, world, prec):
+    """The `config` object -- the same dict in both arms (the driver compares them)."""
+    N, d = wl["N"], wl["d"]
+    return {"workload": wl["name"], "N_per_side": N, "d": d, "kernel_mul": 2.0, "kernel_num": 5,
+            "parallelism": f"row-block x{world}" if world > 1 else "single GPU",
+            "step": "MK_MMD forward + backward (Part A); Part B select measured on the scaled sweep, see roofline.part_b_select"}
+
+
+def reference_mk_mmd():
+    """(callable(x, y) -> loss tensor with autograd graph, kind).  The reference's own MK_MMD from the oracle/_ref copy
+    (baseline legs only), else the port."""
+    from oracle import build_ref, cpu_port
+    if build_ref.available():
+        return build_ref.load_mmd().MK_MMD, "reference"
+    return cpu_port.mk_mmd_graph, "port"
+
+
+def cpu_whole_steps(N, d, seed, max_steps, budget_s):
+    """Whole fwd+bwd steps of the reference MK_MMD on the host cores (all threads): median seconds per step, steps done."""
+    fn, kind = reference_mk_mmd()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = 2 * N
     g = torch.Generator().manual_seed(seed)
-    z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
-    m = 512 if n * d <= 16384 * 512 else 128
-    cpu_port.rowblock_fwd_bwd(z, N, 0, m)            # warm-up
+    x = torch.randn(N, d, generator=g)
+    y = torch.randn(N, d, generator=g) * 1.25 + 0.1
+    xs, ys = x[:512].clone().requires_grad_(True), y[:512].clone().requires_grad_(True)
+    fn(xs, ys).backward()                                   # thread pool / allocator warm-up on a small problem
     times = []
     t_end = time.perf_counter() + budget_s
-    r0 = 0
-    while len(times) < 3 or (time.perf_counter() < t_end and len(times) < 20):
+    while len(times) < max_steps and (not times or time.perf_counter() + statistics.median(times) < t_end):
+        a = x.clone().requires_grad_(True)
+        b = y.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        cpu_port.rowblock_fwd_bwd(z, N, r0, m)
+        fn(a, b).backward()
         times.append(time.perf_counter() - t0)
-        r0 = (r0 + m) % (n - m)
-    t_block = statistics.median(times)
-    full = t_block * (n / m)
-    desc = (f"rows [r0, r0+{m}) of the {n}x{n} problem (d={d}) fwd+bwd with torch CPU ops, median of {len(times)} "
-            f"blocks, x{n // m} blocks per step")
-    return N / full, cores, desc, t_block
+        del a, b
+    return statistics.median(times), len(times), cores, kind
 
 
+# ----------------------------------------------------------------------------------------- CPU arm
 def run_reference(args, rank, world):
     if rank != 0:
         return
     wl = WORKLOADS["sweep8192" if world == 1 else "sharded65536"] if args.workload == "auto" else WORKLOADS[args.workload]
     N, d = wl["N"], wl["d"]
-    from oracle import cpu_port
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     n = 2 * N
-    g = torch.Generator().manual_seed(wl["seed"])
-    z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
-    m = 512 if n * d <= 16384 * 512 else 128
-    for _ in range(max(1, min(args.warmup, 3))):
-        cpu_port.rowblock_fwd_bwd(z, N, 0, m)
-    times = []
-    r0 = 0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        cpu_port.rowblock_fwd_bwd(z, N, r0, m)
-        times.append(time.perf_counter() - t0)
-        r0 = (r0 + m) % (n - m)
-    t_step = (sum(times) / len(times)) * (n / m)       # one full step = n/m such blocks
+    if n * d <= 16384 * 512:
+        # configs[1]: WHOLE steps of the reference's MK_MMD (code/MMD.py:46-74 + autograd), as many of --steps as fit
+        t_step, done, cores, kind = cpu_whole_steps(N, d, wl["seed"], args.steps, args.ref_budget_s)
+        sample = (f"{done} whole fwd+bwd steps of the reference MK_MMD at N={N} per side, d={d} on {cores} host threads "
+                  f"(time budget {args.ref_budget_s:.0f} s; --steps asked for {args.steps})")
+        extra = {"steps_measured": done, "extrapolated": False}
+    else:
+        # configs[3]: no device can hold the reference's n x n activations (773 GB): a row-block sample, extrapolated
+        from oracle import cpu_port
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        g = torch.Generator().manual_seed(wl["seed"])
+        z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
+        m = 128
+        for _ in range(2):
+            cpu_port.rowblock_fwd_bwd(z, N, 0, m)
+        times, r0 = [], 0
+        t_end = time.perf_counter() + args.ref_budget_s
+        while len(times) < args.steps and time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            cpu_port.rowblock_fwd_bwd(z, N, r0, m)
+            times.append(time.perf_counter() - t0)
+            r0 = (r0 + m) % (n - m)
+        t_step = statistics.median(times) * (n / m)
+        done, kind = len(times), "port"
+        sample = (f"rows [r0, r0+{m}) of the {n}x{n} problem (d={d}) fwd+bwd, torch CPU ops ({done} blocks timed), "
+                  f"x{n // m} = one step: EXTRAPOLATED -- the reference cannot run this size on any single device")
+        extra = {"steps_measured": 0, "blocks_measured": done, "extrapolated": True}
     value = N / t_step
-    sample = (f"each step = rows [r0, r0+{m}) of the {n}x{n} problem (d={d}) fwd+bwd, torch CPU ops, "
-              f"time x{n // m} = one full step")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "N_per_side": N, "d": d},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_of(wl, world, None),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 
@@ -343,6 +371,71 @@ def essence_point_extras(peaks):
                                 "what": "topk_rows over [B,T] scores (sorted, indices bit-exact vs torch.topk) + "
                                         "gather_rows of [B,k,D] features; bytes = scores + values/indices + 2 B k D 4"}
     except Exception as exc:   # extras never take the headline down
+        out["error"] = repr(exc)
+    return out
+
+
+def select_roofline(peaks):
+    """Part B of the path: the Essence-Point select (top-k of 100 over rows of 800 proxy-sample scores,
+    code/fusion_net.py:233-238) on the scaled sweep of SURVEY.md 8d -- 2^18 rows x 800, R W 4 bytes = 839 MB, far larger
+    than L2 -- against the measured HBM copy bandwidth.  Algorithmic bytes: R W 4 read + R k 8 written.  `unsorted` is what
+    the path consumes (the reference averages the selected values and discards the indices; edrl_essence_train_fwd calls
+    the select with sorted = 0); `sorted` is torch.topk's output order."""
+    import edrl_b200
+    out = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "peak_source": f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)",
+           "kernel": "topk_sift_kernel<6, true, 2, 8, SORTED> (one warp per row: sample pivot -> survivors -> exact select)",
+           "traffic": profiled_traffic("topk_sift_kernel"),
+           "traffic_note": "DRAM bytes per launch of the unsorted 2^18 x 800 select (ncu --set full, profiles/)"}
+    R, W, k = 1 << 18, 800, 100
+    x = torch.randn(R, W, device="cuda")
+    byts = R * W * 4 + R * k * 8
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, srt in (("unsorted", False), ("sorted", True)):
+        for _ in range(3):
+            edrl_b200.topk_rows(x, k, sorted=srt)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            edrl_b200.topk_rows(x, k, sorted=srt)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        ent = {"ms": ms, "achieved": byts / ms / 1e6, "frac": byts / ms / 1e6 / peaks["hbm_gbs"]}
+        if srt:
+            out["sorted"] = ent
+        else:
+            out.update(ent)
+            out["algorithmic_bytes"] = byts
+            out["workload"] = f"{R} rows x {W}, k = {k}, selection set (unsorted)"
+    del x
+    return out
+
+
+def reference_driver_runs(steps=8):
+    """BASELINE configs[0], [2], [4] through the reference's OWN drivers (fusion_train.py / fusion_test.py, unmodified, from
+    the oracle/_ref copy) on the synthetic scaffolding of examples/ref_scaffold: see examples/run_reference_driver.py."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    out = {}
+    try:
+        import tempfile
+        import run_reference_driver as RD
+        if RD.reference_dir() is None:
+            return {"unavailable": "no oracle/_ref copy of the reference drivers on this box"}
+        keep = tempfile.mkdtemp(prefix="edrl_ckpt_")
+        out["configs2_full_step_batch64"] = {
+            "swapped": RD.run(arm="swapped", driver="fusion_train", device="cuda", batch=64, steps=steps, keep_dir=keep),
+            "reference_ops_same_gpu": RD.run(arm="reference", driver="fusion_train", device="cuda", batch=64, steps=steps)}
+        ck = out["configs2_full_step_batch64"]["swapped"].get("checkpoint")
+        if ck:
+            out["configs4_missing_modality"] = {
+                m: {arm: RD.run(arm=arm, driver="fusion_test", device="cuda", batch=64, steps=6, missing=m, checkpoint=ck)
+                    for arm in ("swapped", "reference")} for m in ("oct", "fundus")}
+        out["configs0_cpu_whole_model_batch4"] = RD.run(arm="reference", driver="fusion_train", device="cpu", batch=4, steps=3)
+        out["note"] = ("the drivers are data-loader bound at these sizes (numpy noise views and pageable H2D copies in the "
+                       "reference's own loop): `step_period_ms` is the whole loop, `model_forward_ms` the device time of one "
+                       "MedFusion.forward; stand-in encoders, synthetic data, random init")
+    except Exception as exc:
         out["error"] = repr(exc)
     return out
 
@@ -453,7 +546,7 @@ def sweep_vs_torch_gpu(prec):
     from oracle import cpu_port
     out = []
     try:
-        for (N, d) in ((64, 3072), (256, 512), (1024, 512), (4096, 512), (8192, 512)):
+        for (N, d) in ((64, 3072), (256, 512), (512, 512), (1024, 512), (2048, 512), (4096, 512), (8192, 512)):
             x, y = make_inputs(N, d, 1000 + int(math.log2(N)), "cuda")
 
             def ours():
@@ -508,9 +601,14 @@ def run_ours(args, rank, local_rank, world):
     sharded = world > 1
 
     if sharded:
+        # every rank draws the whole problem from the one seed and keeps its row slice, so that rank 0 can evaluate the
+        # same inputs unsharded (anchor + parity)
         assert N % world == 0
         nl = N // world
-        x, y = make_inputs(nl, d, wl["seed"] + rank, dev)
+        xf, yf = make_inputs(N, d, wl["seed"], dev)
+        x, y = xf[rank * nl:(rank + 1) * nl].clone(), yf[rank * nl:(rank + 1) * nl].clone()
+        del xf, yf
+        torch.cuda.empty_cache()
     else:
         nl = N
         x, y = make_inputs(N, d, wl["seed"], dev)
@@ -703,28 +801,86 @@ def run_ours(args, rank, local_rank, world):
                     "peak_source": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)",
                     "algorithmic_flops": flops_b, "mma_per_product": mma_per_product,
                     "executed_tensor_flops": (2.0 * n * n * d * math.ceil(d / 256) + 2.0 * n * n * d) * 3}
-        if sharded:
-            one = (g_ms + 0.0) if prec in ("tf32", "tf32h", "f16s") else (f_ms + b_ms)
+    # ---- N > 1: the same workload on ONE GPU through the same public API (the anchor of the scaling curve), and the
+    #      sharded result checked against it in this very run (the NCCL parity test needs >= 2 GPUs, the test box has 1)
+    parity = None
+    if sharded:
+        gr = torch.Generator().manual_seed(7)
+        rows_l = torch.randint(0, nl, (256,), generator=gr).to(dev)        # the same local row numbers on every rank
+        x.grad = None
+        y.grad = None
+        l_sh = loss_fn(x, y)
+        l_sh.backward()
+        torch.cuda.synchronize()
+        mine = torch.cat([x.grad[rows_l], y.grad[rows_l]]).contiguous()     # [512, d]
+        my_loss = l_sh.detach()
+        gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, gathered, dst=0)
+        if rank == 0:
+            xa.requires_grad_(True)
+            ya.requires_grad_(True)
+
+            def single_step():
+                xa.grad = None
+                ya.grad = None
+                edrl_b200.MK_MMD(xa, ya, precision=prec).backward()
+
+            single_step()
+            one = timed_steps(single_step, 3, 1, flush, 1) / 3
+            with torch.no_grad():
+                single_loss = edrl_b200.MK_MMD(xa, ya, precision=prec).item()
             base = {"n_gpus": 1, "ms_per_step": one, "value": N / (one * 1e-3),
-                    "note": "same workload, unsharded, on rank 0 alone through the C-ABI (fused pass in TF32 mode; "
-                            "the O(nd) apply_grad kernel is not included)"}
+                    "note": "same workload, unsharded, on rank 0 alone through the same public API "
+                            "(edrl_b200.MK_MMD + backward, apply_grad included)"}
+            gmax = max(xa.grad.abs().max().item(), ya.grad.abs().max().item())
+            gerr = 0.0
+            for rk in range(world):
+                ref_rows = torch.cat([xa.grad[rk * nl + rows_l], ya.grad[rk * nl + rows_l]])
+                gerr = max(gerr, (gathered[rk] - ref_rows).abs().max().item())
+            parity = {"loss_sharded": my_loss.item(), "loss_single_gpu": single_loss,
+                      "loss_rel_err": abs(my_loss.item() - single_loss) / abs(single_loss),
+                      "grad_max_err_over_gmax": gerr / gmax, "rows_sampled_per_rank": 512,
+                      "what": "sharded loss and 512 sampled gradient rows of every rank against the single-GPU evaluation of "
+                              "the same inputs in the same run (same kernels, different work lists: agreement to fp32 "
+                              "summation order); the single-GPU kernel itself is checked against the fp64 row-blocked "
+                              "oracle at this size in tests/test_gpu_mmd.py",
+                      "ok": bool(abs(my_loss.item() - single_loss) <= 1e-5 * abs(single_loss) and gerr <= 1e-4 * gmax)}
+            xa.requires_grad_(False)
+            ya.requires_grad_(False)
     if world > 1:
         dist.barrier()
 
     if rank == 0:
         if args.no_cpu_baseline:
-            cpu_v, cores, sample = None, 0, "skipped (--no-cpu-baseline, profiling run)"
+            cpu_v, cores, sample, cpu_kind = None, 0, "skipped (--no-cpu-baseline, profiling run)", "port"
+        elif not sharded:
+            t_cpu, done, cores, cpu_kind = cpu_whole_steps(N, d, wl["seed"], 2, 30.0)
+            cpu_v = N / t_cpu
+            sample = (f"{done} whole fwd+bwd step(s) of the reference MK_MMD (code/MMD.py:46-74 + autograd) at N={N} per side, "
+                      f"d={d}: {t_cpu:.2f} s per step on {cores} host threads")
         else:
-            cpu_v, cores, sample, _ = cpu_port_sample(N, d, wl["seed"])
+            from oracle import cpu_port
+            cores, cpu_kind = os.cpu_count() or 1, "port"
+            torch.set_num_threads(cores)
+            g = torch.Generator().manual_seed(wl["seed"])
+            z = torch.cat([torch.randn(N, d, generator=g), torch.randn(N, d, generator=g) * 1.25 + 0.1])
+            cpu_port.rowblock_fwd_bwd(z, N, 0, 128)
+            ts = []
+            for i in range(5):
+                t0 = time.perf_counter()
+                cpu_port.rowblock_fwd_bwd(z, N, 128 * i, 128)
+                ts.append(time.perf_counter() - t0)
+            cpu_v = N / (statistics.median(ts) * (2 * N / 128))
+            sample = (f"EXTRAPOLATED: rows [r0, r0+128) of the {2 * N}x{2 * N} problem (d={d}) fwd+bwd with torch CPU ops, median "
+                      f"of 5 blocks x{2 * N // 128}; the reference cannot run this size on any single device")
         extras = {} if (args.no_extras or sharded) else essence_point_extras(peaks)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": prec, "data": "synthetic",
-            "config": {"workload": wl["name"], "N_per_side": N, "d": d, "kernel_mul": 2.0, "kernel_num": 5,
-                       "precision": prec, "parallelism": f"row-block x{world}" if sharded else "single GPU",
-                       "l2": "256 MiB memset between steps (untimed); per-step CUDA events",
+            "config": config_of(wl, world, prec),
+            "timing": {"precision": prec, "l2": "256 MiB memset between steps (untimed); per-step CUDA events",
                        "host_cpus_bound": bound_cpus},
             "clocks": clocks,
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -737,13 +893,24 @@ def run_ours(args, rank, local_rank, world):
                            "how": "same step, copies and compute back to back on one stream, per-step events"},
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_fwd": fwd_info, "roofline_bwd_separate": bwd_info,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": cpu_kind, "sample": sample},
         }
+        if roof is not None:
+            roof["part_a"] = {k: roof[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic", "ms")
+                              if k in roof}
+            if not sharded:
+                try:
+                    roof["part_b_select"] = select_roofline(peaks)
+                except Exception as exc:
+                    roof["part_b_select"] = {"error": repr(exc)}
+        if parity:
+            line["parity"] = parity
         if base:
             line["strong_scaling_base"] = base
-            line["note"] = ("N>1 runs configs[3] (fixed total work, strong scaling); the 1-GPU time of the SAME workload is "
-                            "strong_scaling_base, while `bench.py --gpus 1` runs configs[1] (N=8192, d=512) as the contract "
-                            "asks, so per-N values are comparable only against strong_scaling_base")
+            line["note"] = ("N>1 runs configs[3] (fixed total work, strong scaling); the 1-GPU time of the SAME workload through "
+                            "the same API is strong_scaling_base (and `scale_anchor` of the N=1 line), while `bench.py --gpus 1` "
+                            "runs configs[1] (N=8192, d=512) as the contract asks: per-N values compare with "
+                            "strong_scaling_base, not with the N=1 line's value")
         if extras:
             line["essence_point"] = extras
             line["sweep_vs_torch_gpu"] = sweep_vs_torch_gpu(prec)
@@ -792,6 +959,30 @@ def run_ours(args, rank, local_rank, world):
                 "split, fp32-level accuracy, first-generation kernels.")
             line["essence_path_vs_torch_gpu"] = essence_path_vs_torch_gpu()
             line["eval_missing_modality"] = eval_missing_modality()
+            # the configs[3] workload (N = 65536 per side, d = 1024) on this one GPU through the same public API: the anchor
+            # the N > 1 lines' values compare with (the driver's own curve divides by THIS line's `value`, which is the
+            # configs[1] workload, as the contract asks)
+            try:
+                wa = WORKLOADS["sharded65536"]
+                xs_, ys_ = make_inputs(wa["N"], wa["d"], wa["seed"], dev)
+                xs_.requires_grad_(True)
+                ys_.requires_grad_(True)
+
+                def anchor_step():
+                    xs_.grad = None
+                    ys_.grad = None
+                    edrl_b200.MK_MMD(xs_, ys_, precision=prec).backward()
+
+                anchor_step()
+                t = timed_steps(anchor_step, 3, 1, flush, 1) / 3
+                line["scale_anchor"] = {"workload": wa["name"], "n_gpus": 1, "ms_per_step": t, "value": wa["N"] / (t * 1e-3),
+                                        "note": "N > 1 lines run this workload sharded: compare their `value` with this one"}
+                del xs_, ys_
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                line["scale_anchor"] = {"error": repr(exc)}
+            if not args.no_drivers:
+                line["reference_drivers"] = reference_driver_runs()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -806,6 +997,8 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32h", "f16s", "3xtf32"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-drivers", action="store_true", help="skip the reference-driver runs (configs[0], [2], [4]) of the extras")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -63,6 +63,8 @@ def run(arm="swapped", driver="fusion_train", device="cuda", batch=64, steps=12,
     n_train = batch * steps
     # KFold(5): 80 % train; the val / test loader wants at least one full batch of 16 (drop_last, code/fusion_train.py:593)
     n_files = max((n_train * 5 + 3) // 4 + 5, 85)
+    if driver == "fusion_test":
+        n_files = max(n_files, 5 * 16 * max(steps, 4) + 5)     # `steps` full evaluation batches of 16
     work = workdir or tempfile.mkdtemp(prefix="edrl_driver_")
     os.makedirs(os.path.join(work, "Your_train_path"), exist_ok=True)
     for i in range(n_files):
@@ -110,7 +112,12 @@ def run(arm="swapped", driver="fusion_train", device="cuda", batch=64, steps=12,
         err = None
         with contextlib.redirect_stdout(out if quiet else sys.stdout), contextlib.redirect_stderr(out if quiet else sys.stderr):
             stdin = sys.stdin
-            sys.stdin = open(os.devnull)                        # fusion_test.py ends in pdb.set_trace(): EOF quits it
+            sys.stdin = open(os.devnull)
+            import pdb
+            set_trace = pdb.set_trace
+            # fusion_test.py ends in a stray `import pdb; pdb.set_trace()` (code/fusion_test.py:759-760) after test() has
+            # returned: a debugger prompt has no place in a batch run (under pytest it would wait for a terminal forever)
+            pdb.set_trace = lambda *a, **k: None
             try:
                 runpy.run_path(argv[0], run_name="__main__")
             except SystemExit:
@@ -119,6 +126,7 @@ def run(arm="swapped", driver="fusion_train", device="cuda", batch=64, steps=12,
                 if type(exc).__name__ != "BdbQuit":
                     err = f"{type(exc).__name__}: {exc}"
             finally:
+                pdb.set_trace = set_trace
                 sys.stdin.close()
                 sys.stdin = stdin
         if device == "cuda":

@@ -1844,35 +1844,27 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
   static const bool novec = (getenv("EDRL_TOPK_VEC") != nullptr && atoi(getenv("EDRL_TOPK_VEC")) == 0);
   static const bool nosift = (getenv("EDRL_TOPK_SIFT") != nullptr && atoi(getenv("EDRL_TOPK_SIFT")) == 0);
-  static const int sift_g = getenv("EDRL_TOPK_SIFT_G") ? atoi(getenv("EDRL_TOPK_SIFT_G")) : 0;   // A/B: 16 or 32 only
-  if (uniform && Wmax >= 128 && Wmax <= 2048 && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
-    // sift select (topk_sift.cuh): sample pivot -> survivors -> exact select, when the sampling plan fits the list;
-    // a half-warp per row up to 1024 elements, a warp per row above
+  if (uniform && Wmax >= 512 && Wmax <= 2048 && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
+    // sift select (topk_sift.cuh): sample pivot -> survivors -> exact select, when the sampling plan fits the list
     const int W4 = Wmax >> 2;
     bool done = false;
-#define EDRL_SIFT_CASE(G_, FI_, P_, SSTR_, SL_)                                                                      \
-  if (!done && (sift_g == 0 || sift_g == G_) && W4 / G_ == FI_ && ((W4 % G_) != 0) == P_) {                          \
-    const SiftPlan sp = sift_plan(Wmax, k, G_ * ((FI_ * 4 + SSTR_ - 1) / SSTR_), G_ * SL_);                         \
+#define EDRL_SIFT_CASE(FI_, P_, SSTR_, SL_)                                                                          \
+  if (!done && W4 / 32 == FI_ && ((W4 % 32) != 0) == P_) {                                                           \
+    const SiftPlan sp = sift_plan(Wmax, k, 32 * ((FI_ * 4 + SSTR_ - 1) / SSTR_), 32 * SL_);                         \
     if (sp.ok) {                                                                                                      \
-      const int rpb = 4 * (32 / G_);                                                                                  \
-      const int grid = (R + rpb - 1) / rpb;                                                                           \
+      const int grid = (R + 3) / 4;                                                                                   \
       if (sorted)                                                                                                     \
-        topk_sift_kernel<G_, FI_, P_, SSTR_, SL_, true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+        topk_sift_kernel<FI_, P_, SSTR_, SL_, true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
       else                                                                                                            \
-        topk_sift_kernel<G_, FI_, P_, SSTR_, SL_, false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+        topk_sift_kernel<FI_, P_, SSTR_, SL_, false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
       done = true;                                                                                                    \
     }                                                                                                                 \
   }
-    EDRL_SIFT_CASE(16, 2, true, 1, 8)       // W = 144 (fundus token rows)
-    EDRL_SIFT_CASE(16, 3, true, 1, 8)       // W = 216 (OCT token rows)
-    EDRL_SIFT_CASE(16, 4, false, 1, 16)     // W = 256
-    EDRL_SIFT_CASE(16, 8, false, 2, 16)     // W = 512
-    EDRL_SIFT_CASE(16, 12, true, 2, 16)     // W = 800 (the reference's S)
-    EDRL_SIFT_CASE(16, 16, false, 3, 16)    // W = 1024
-    EDRL_SIFT_CASE(32, 6, true, 2, 8)       // W = 800, a warp per row (A/B: EDRL_TOPK_SIFT_G=32)
-    EDRL_SIFT_CASE(32, 8, false, 2, 16)     // W = 1024, large k
-    EDRL_SIFT_CASE(32, 12, true, 3, 16)     // W = 1600 (C = 3 negatives)
-    EDRL_SIFT_CASE(32, 16, false, 4, 16)    // W = 2048
+    EDRL_SIFT_CASE(4, false, 1, 8)       // W = 512
+    EDRL_SIFT_CASE(6, true, 2, 8)        // W = 800 (the reference's S)
+    EDRL_SIFT_CASE(8, false, 2, 8)       // W = 1024
+    EDRL_SIFT_CASE(12, true, 2, 8)       // W = 1600 (C = 3 negatives)
+    EDRL_SIFT_CASE(16, false, 2, 8)      // W = 2048
 #undef EDRL_SIFT_CASE
     if (done) {
       EDRL_LAUNCHED();

@@ -1,4 +1,4 @@
-// K7d "sift" select: top-k of a row by a GROUP of G = 16 or 32 lanes (two rows or one per warp), built around the
+// K7d "sift" select: top-k of a row by one warp (G = 32 lanes; the helpers are written for a group of G), built around the
 // instruction count -- the select is bound by instruction issue and by shared-memory wavefronts, not by HBM (ncu on
 // topk_vec_kernel: 87 % issue-active, 41 % DRAM).  Included by eprl.cu after the row accessors, emit_winners() and
 // radix_select_row_slow().
@@ -17,8 +17,11 @@
 //          histogram between p and the row maximum, the threshold bin's (<= 32) values ranked against each other with
 //          shuffles by (value descending, index ascending) -- which IS the tie rule, so there is no separate tie path --
 //          winners above the bin compacted, the ranked candidates appended behind them;
-//   * for rows of up to 1024 elements a HALF-warp owns a row: every shuffle, vote, scan step and histogram walk of the
-//     per-row overhead is issued once for two rows, which halves the dominant term.
+// Measured and dropped: a half-warp per row (every shuffle, vote and scan step issued once for two rows; with 16
+// survivor slots and 4 histogram bins per lane the per-row instruction count did not drop: 46 % of HBM against 57 %), and
+// persistent warps that issue the next row's loads under the exact select of the current one (same time as one row per
+// warp at equal occupancy, 0.332 against 0.329 ms on 2^18 x 800 -- and the registers it needs cost two resident blocks
+// per SM, which costs more: the kernel lives on occupancy, 0.281 ms at 8 blocks per SM).
 // Every bin index is a monotone function of the value (one FFMA: y = fma(x, scale, off) with off = 2^23 + 1 - lo * scale
 // rounded once; the bin is y's low mantissa bits), which is all the select needs: bin(a) > bin(b) implies a > b.
 // Anything irregular -- NaN or +inf in the row (NaN-propagating 3-input max), a constant or non-finite sample, a pivot
@@ -181,78 +184,6 @@ __device__ __forceinline__ bool walk_from_top(const unsigned int *hist, int need
   return L >= 0;
 }
 
-// descending bitonic network over TOT = G * NPL 32-bit composites, NPL per lane at positions gl * NPL + i
-template <int G, int NPL>
-__device__ __forceinline__ void bitonic_desc(uint32_t (&c)[NPL], int gl) {
-  constexpr int TOT = G * NPL;
-#pragma unroll
-  for (int size = 2; size <= TOT; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= NPL) {
-        const int lx = stride / NPL;
-        const bool lower = (gl & lx) == 0;
-        const bool desc = (size >= TOT) ? true : (((gl * NPL) & size) == 0);
-        const bool keep_max = (lower == desc);
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const uint32_t o = __shfl_xor_sync(FULL, c[i], lx);
-          c[i] = keep_max ? max(c[i], o) : min(c[i], o);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          if ((i & stride) == 0) {
-            const int p2 = i | stride;
-            const bool desc = (size >= TOT) ? true : (((gl * NPL + i) & size) == 0);
-            const uint32_t a = c[i], b = c[p2];
-            const uint32_t hi = max(a, b), lo = min(a, b);
-            c[i] = desc ? hi : lo;
-            c[p2] = desc ? lo : hi;
-          }
-        }
-      }
-    }
-  }
-}
-
-// Winners of one row (buf[0, k): .x = ~index, .y = value bits; zeros behind them) to global memory by a half-warp, in
-// torch.topk's order, through the 32-bit composites (key - key(T)) << 7 | (127 - slot) -- valid when the winners' keys
-// span < 2^25 and no two are equal.  false: nothing written, this group must go through the full-warp emit_winners
-// (or had nothing to emit: !ok).  Every lane of the warp calls this.
-__device__ __forceinline__ bool emit_sorted_half(bool ok, const uint2 *buf, int k, int lane, uint32_t tkey, uint32_t xkey,
-                                                 float *__restrict__ vrow, int *__restrict__ irow) {
-  const int gl = lane & 15;
-  uint32_t c[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int sl = gl * 8 + i;
-    const uint32_t kk = f2key_fast(__uint_as_float(buf[sl].y)) - tkey;
-    c[i] = (sl < k) ? ((kk << 7) | (uint32_t)(127 - sl)) : 0u;
-  }
-  bitonic_desc<16, 8>(c, gl);
-  const uint32_t nxt0 = __shfl_down_sync(FULL, c[0], 1, 16);
-  bool dup = false;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t nx = (i < 7) ? c[(i + 1) & 7] : nxt0;
-    const bool last = (i == 7) && (gl == 15);
-    dup = dup || (!last && gl * 8 + i + 1 < k && (c[i] >> 7) == (nx >> 7));
-  }
-  const bool good = ok && (group_ballot<16>(dup, lane) == 0u) && (xkey - tkey < (1u << 25));
-  if (!good) return false;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int p2 = gl * 8 + i;
-    if (p2 < k) {
-      const uint2 w = buf[127 - (int)(c[i] & 127u)];
-      vrow[p2] = __uint_as_float(w.y);
-      irow[p2] = (int)~w.x;
-    }
-  }
-  return true;
-}
-
 // Stage 3: exact top-k of the C survivors in list[0, C) (uint2: .x = ~index, .y = value bits; all values in [p, rowmax],
 // k <= C <= G SL) by the group.  On success the winners are in list[0, k) (list[k, 128) zero when SORTED) and T is the
 // k-th largest value; `list` is reused as the winners' buffer once its entries are in registers.  false: crowded
@@ -328,7 +259,9 @@ __device__ __forceinline__ bool select_survivors(bool active, uint2 *list, uint2
         : "memory");
   }
   __syncwarp();
-  // rank the candidates by (value descending, index ascending): the first `rem` of that order win
+  // rank the candidates by (value descending, index ascending): the first `rem` of that order win.  Every lane walks
+  // the candidate list in shared memory (broadcast loads, independent of one another: they pipeline, where a shuffle
+  // per candidate and operand did not) and counts the entries that come before its own.
   uint2 me[CPL];
   int rank[CPL];
 #pragma unroll
@@ -337,26 +270,15 @@ __device__ __forceinline__ bool select_survivors(bool active, uint2 *list, uint2
     me[q] = have ? cand[q * G + gl] : make_uint2(0u, 0xff800000u);       // (-inf, index 2^32 - 1: behind everything)
     rank[q] = 0;
   }
-  int cmax = ok ? cntb : 0;                                  // the loop bound must be warp-uniform: the larger group's
-  if (G < 32) cmax = max(cmax, __shfl_xor_sync(FULL, cmax, 16));
-  const int gbase = lane & ~(G - 1);
-  for (int j = 0; j < cmax; ++j) {
-    const int src = gbase + (j & (G - 1));
-    float ov;
-    uint32_t ox;
-    if (CPL == 1) {
-      ov = __shfl_sync(FULL, __uint_as_float(me[0].y), src);
-      ox = __shfl_sync(FULL, me[0].x, src);
-    } else {
-      const bool second = j >= G;                            // (uniform across the warp)
-      ov = __shfl_sync(FULL, __uint_as_float(second ? me[CPL - 1].y : me[0].y), src);
-      ox = __shfl_sync(FULL, second ? me[CPL - 1].x : me[0].x, src);
-    }
-    // (a group with fewer candidates than cmax reads its own padding: -inf, behind everything -- no effect)
+  const int cn = ok ? cntb : 0;
+#pragma unroll 4
+  for (int j = 0; j < cn; ++j) {
+    const uint2 o = cand[j];
+    const float ov = __uint_as_float(o.y);
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
       const float cv = __uint_as_float(me[q].y);
-      rank[q] += (ov > cv || (ov == cv && ox > me[q].x)) ? 1 : 0;        // .x = ~index: larger = lower index = earlier
+      rank[q] += (ov > cv || (ov == cv && o.x > me[q].x)) ? 1 : 0;       // .x = ~index: larger = lower index = earlier
     }
   }
   float tv = __int_as_float(0xff800000);
@@ -412,38 +334,32 @@ __device__ __forceinline__ bool sample_pivot(bool ok, const float (&sv)[NS], uns
 
 }  // namespace sift
 
-// A group of G lanes per row (32 / G rows per warp, 4 warps per block), uniform width W = 4 (G FI + partial lanes), the
-// row in registers (LDG.128), k <= 128.  SSTR: sampling stride over the lane's full-iteration elements; SL: survivor
-// slots per lane (capacity CAP = G SL >= 128).
-template <int G, int FI, bool PARTIAL, int SSTR, int SL, bool SORTED, class Rows>
+// One warp per row: uniform width W = 4 (32 FI + partial lanes) <= 2048, the row in registers (LDG.128), k <= 128.
+// SSTR: sampling stride over the lane's full-iteration elements; SL: survivor slots per lane (capacity 32 SL >= 128).
+template <int FI, bool PARTIAL, int SSTR, int SL, bool SORTED, class Rows>
 __global__ void __launch_bounds__(128, (FI * 4 + SL * 2 <= 44) ? 8 : 4)
 topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict__ vals, int *__restrict__ idx) {
+  constexpr int G = 32;
   constexpr int NI = FI + (PARTIAL ? 1 : 0);
   constexpr int E = NI * 4;
   constexpr int NS = (FI * 4 + SSTR - 1) / SSTR;
   constexpr int CAP = G * SL;
-  constexpr int RPW = 32 / G;                                // rows per warp
-  static_assert(G == 16 || G == 32, "sift select: half-warp or warp per row");
   static_assert(FI >= 2 && NS >= 4 && CAP >= 128, "sift select: row too narrow / list too small for the winners' buffer");
-  __shared__ __align__(16) uint2 s_list[4 * RPW][CAP];       // per row: survivors, later the winners (first 128)
-  __shared__ __align__(16) uint2 s_cand[4 * RPW][32];
-  __shared__ __align__(16) unsigned int s_hist[4 * RPW][sift::SBINS];
+  __shared__ __align__(16) uint2 s_list[4][CAP];             // per warp: survivors, later the winners (first 128)
+  __shared__ __align__(16) uint2 s_cand[4][32];
+  __shared__ __align__(16) unsigned int s_hist[4][sift::SBINS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gl = lane & (G - 1), grp = lane / G;
-  const int r_raw = (blockIdx.x * 4 + wib) * RPW + grp;
-  if ((blockIdx.x * 4 + wib) * RPW >= R) return;             // whole warp past the end
-  const bool active = r_raw < R;
-  const int r = active ? r_raw : R - 1;                      // an idle half keeps the shuffles company on the last row
-  const int slot = wib * RPW + grp;
-  uint2 *list = s_list[slot];
+  const int r = blockIdx.x * 4 + wib;
+  if (r >= R) return;
+  uint2 *list = s_list[wib];
   const typename Rows::Cursor cur = rows.cursor(r);
-  const bool pvalid = PARTIAL && gl < ((W >> 2) % G);
+  const bool pvalid = PARTIAL && lane < ((W >> 2) & 31);
   float x[E];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const float ninf = __int_as_float(0xff800000);           // lanes without data: below every pivot
     float4 v = make_float4(ninf, ninf, ninf, ninf);
-    if (i < FI || pvalid) v = __ldg(reinterpret_cast<const float4 *>(cur.at((i * G + gl) * 4)));
+    if (i < FI || pvalid) v = __ldg(reinterpret_cast<const float4 *>(cur.at((i * G + lane) * 4)));
     x[4 * i + 0] = v.x;
     x[4 * i + 1] = v.y;
     x[4 * i + 2] = v.z;
@@ -455,23 +371,21 @@ topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict_
   for (int e = 1; e + 1 < E; e += 2) mx = sift::max3_nan(mx, x[e], x[e + 1]);
   mx = sift::max2_nan(mx, x[E - 1]);
   mx = sift::group_max_nan<G>(mx);
-  bool ok = active && (mx < __int_as_float(0x7f800000));
+  bool ok = mx < __int_as_float(0x7f800000);
   float sv[NS];
 #pragma unroll
   for (int i = 0; i < NS; ++i) sv[i] = x[i * SSTR];
   float p;
-  ok = sift::sample_pivot<G, NS>(ok, sv, s_hist[slot], jtarget, lane, p);
+  ok = sift::sample_pivot<G, NS>(ok, sv, s_hist[wib], jtarget, lane, p);
   int cnt = 0;
 #pragma unroll
   for (int e = 0; e < E; ++e) cnt += (x[e] >= p) ? 1 : 0;
   const int incl = sift::group_incl_scan<G>(cnt);
-  const int C = __shfl_sync(sift::FULL, incl, (lane & ~(G - 1)) + G - 1);
+  const int C = __shfl_sync(sift::FULL, incl, 31);
   ok = ok && C >= k && C <= CAP;
-  {
-    // the storing pass; a row that is not ok stores nothing (+inf pivot)
-    const float ps = ok ? p : __int_as_float(0x7f800000);
+  if (ok) {                                                  // (warp-uniform)
     uint32_t pos = (uint32_t)__cvta_generic_to_shared(list) + 8u * (uint32_t)(incl - cnt);
-    const uint32_t ngl4 = ~((uint32_t)gl << 2);              // ~(4 gl + c) = ~(4 gl) - c
+    const uint32_t nlane4 = ~((uint32_t)lane << 2);          // ~(4 lane + c) = ~(4 lane) - c
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       asm volatile(
@@ -482,54 +396,18 @@ topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict_
           "@q add.u32 %0, %0, 8;\n\t"
           "}\n"
           : "+r"(pos)
-          : "r"(ngl4 - (uint32_t)((e >> 2) * (4 * G) + (e & 3))), "f"(x[e]), "f"(ps), "r"(__float_as_uint(x[e]))
+          : "r"(nlane4 - (uint32_t)((e >> 2) * (4 * G) + (e & 3))), "f"(x[e]), "f"(p), "r"(__float_as_uint(x[e]))
           : "memory");
     }
   }
   __syncwarp();
   float T;
-  ok = sift::select_survivors<G, SL, SORTED>(ok, list, s_cand[slot], s_hist[slot], C, p, mx, k, lane, T) && ok;
-  float *vrow = vals + (size_t)r * k;
-  int *irow = idx + (size_t)r * k;
-  if (G == 32) {
-    if (ok) {
-      emit_winners<SORTED>(list, k, lane, f2key_fast(T), f2key_fast(mx), vrow, irow);
-    } else if (active) {
-      // (radix_select_row_slow wants 256 words of histogram that later hold 128 64-bit winners: the survivors' list)
-      radix_select_row_slow<E, SORTED, Rows>(rows, r, k, reinterpret_cast<unsigned int *>(list), lane, vals, idx);
-    }
+  ok = sift::select_survivors<G, SL, SORTED>(ok, list, s_cand[wib], s_hist[wib], C, p, mx, k, lane, T);
+  if (ok) {
+    emit_winners<SORTED>(list, k, lane, f2key_fast(T), f2key_fast(mx), vals + (size_t)r * k, idx + (size_t)r * k);
   } else {
-    bool emitted = false;
-    if (SORTED) {
-      emitted = sift::emit_sorted_half(ok, list, k, lane, f2key_fast(T), f2key_fast(mx), vrow, irow);
-    } else if (ok) {
-      for (int t2 = gl; t2 < k; t2 += G) {
-        const uint2 cc = list[t2];
-        vrow[t2] = __uint_as_float(cc.y);
-        irow[t2] = (int)~cc.x;
-      }
-      emitted = true;
-    }
-    // what is left takes the whole warp, one row after the other: a sorted emit through the 64-bit network (equal
-    // keys among the winners, or keys spanning more than 2^25), or the slow select for a row that fell out on the way
-    const uint32_t todo_emit = __ballot_sync(sift::FULL, active && ok && !emitted);
-    const uint32_t todo_slow = __ballot_sync(sift::FULL, active && !ok);
-#pragma unroll
-    for (int g2 = 0; g2 < RPW; ++g2) {
-      const int src = g2 * G;
-      if ((todo_emit >> src) & 1u) {
-        const float Tg = __shfl_sync(sift::FULL, T, src), mg = __shfl_sync(sift::FULL, mx, src);
-        const int rg = __shfl_sync(sift::FULL, r, src);
-        emit_winners<SORTED>(s_list[wib * RPW + g2], k, lane, f2key_fast(Tg), f2key_fast(mg), vals + (size_t)rg * k,
-                             idx + (size_t)rg * k);
-      } else if ((todo_slow >> src) & 1u) {
-        const int rg = __shfl_sync(sift::FULL, r, src);
-        __syncwarp();
-        // (the whole warp on one row: half as many elements per lane)
-        radix_select_row_slow<E / 2, SORTED, Rows>(rows, rg, k, reinterpret_cast<unsigned int *>(s_list[wib * RPW + g2]),
-                                                   lane, vals, idx);
-      }
-    }
+    // (radix_select_row_slow wants 256 words of histogram that later hold 128 64-bit winners: the survivors' list)
+    radix_select_row_slow<E, SORTED, Rows>(rows, r, k, reinterpret_cast<unsigned int *>(list), lane, vals, idx);
   }
 }
 

@@ -18,8 +18,9 @@ for (R, W, k) in ((1 << 18, 800, 100), (1 << 17, 1600, 100), (1 << 18, 1024, 100
         ms = a.elapsed_time(b) / 10
         byts = R * W * 4 + R * k * 8
         print(f"R={R} W={W} k={k} sorted={s}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s  {byts/ms/1e6/peak*100:.1f}% of HBM")
+    sv, si = torch.sort(x[:4096], dim=1, descending=True, stable=True)      # ties: lowest index first
+    tv, ti = sv[:, :k], si[:, :k]
     v, i = edrl_b200.topk_rows(x[:4096], k, sorted=True)
-    tv, ti = torch.topk(x[:4096], k, dim=1)
     assert torch.equal(v, tv) and torch.equal(i.long(), ti), "sorted mismatch"
     v, i = edrl_b200.topk_rows(x[:4096], k, sorted=False)
     assert torch.equal(v.sort(dim=1, descending=True).values, tv) and torch.equal(i.long().sort(dim=1).values, ti.sort(dim=1).values)
