@@ -115,6 +115,13 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int lane) {
   return (G == 32) ? b : ((b >> (lane & 16)) & 0xffffu);
 }
 
+// Counting x >= p without predicates (ptxas parks every predicate of an unrolled compare chain in a bit mask, five
+// instructions per element instead of two): the sign bit of x - p is 0 exactly when x >= p (IEEE subtraction has the sign
+// of the true difference, denormals included; a -inf pad gives -inf), and one funnel shift appends it to an accumulator.
+// After n elements: n - popc(acc) of them were >= p.
+__device__ __forceinline__ void push_sign(uint32_t &acc, float x, float p) {
+  acc = __funnelshift_l(__float_as_uint(x - p), acc, 1);
+}
 // The affine map of a value histogram over [lo, hi]: bin(x) = low bits of fma(x, scale, off), in [0, SBINS - 1] for
 // lo <= x <= hi (the range maps onto SBINS - 3 bins, + 1 of offset, +- 1/2 for each of the two roundings).  ok = false
 // when the range is empty / not finite or too narrow for `lo * scale` to keep integer precision (|lo| scale >= 2^22).
@@ -207,30 +214,37 @@ __device__ __forceinline__ bool select_survivors(bool active, uint2 *list, uint2
   uint32_t yb[SL];                                           // bin code of slot i, 0 for an empty slot (below every bin)
 #pragma unroll
   for (int i = 0; i < SL; ++i) {
+    // (an empty slot counts into the spare word behind the bins: a predicated reduction becomes a branch region around
+    //  the warp-aggregated ATOMS, four instructions instead of two)
     const uint32_t y = __float_as_uint(fmaf(__uint_as_float(s[i].y), bm.scale, bm.off));
     asm volatile(
         "{\n\t"
         ".reg .pred q;\n\t"
+        ".reg .b32 a;\n\t"
         "setp.lt.s32 q, %2, %3;\n\t"
-        "@q red.shared.add.u32 [%1], 1;\n\t"
+        "selp.b32 a, %1, %5, q;\n\t"
+        "red.shared.add.u32 [a], 1;\n\t"
         "selp.b32 %0, %4, 0, q;\n\t"
         "}\n"
         : "=r"(yb[i])
-        : "r"((y << 2) + hbase), "r"(i), "r"(nv), "r"(y)
+        : "r"((y << 2) + hbase), "r"(i), "r"(nv), "r"(y), "r"(hist_addr + 4u * SBINS)
         : "memory");
   }
   __syncwarp();
   int bin, cntb, rem;
   ok = walk_from_top<G>(hist, k, lane, bin, cntb, rem) && ok;
   ok = ok && cntb <= 32 && rem >= 1 && rem <= cntb;
-  const uint32_t yt = ok ? 0x4b000000u + (uint32_t)bin : 0xffffffffu;     // not ok: nothing is above or in the bin
-  // winners above the threshold bin and the bin's candidates: lane-local counts, one group prefix for both
-  int cw = 0, cc = 0;
+  const uint32_t yt = ok ? 0x4b000000u + (uint32_t)bin : 0x7fffffffu;     // not ok: nothing is above or in the bin
+  // winners above the threshold bin and the bin's candidates: lane-local counts, one group prefix for both.  Sign bits
+  // again (bin codes are < 2^31): yt - y < 0 above the bin, yt - y - 1 < 0 in or above it.
+  uint32_t above = 0u, notbelow = 0u;
 #pragma unroll
   for (int i = 0; i < SL; ++i) {
-    cw += (yb[i] > yt) ? 1 : 0;
-    cc += (yb[i] == yt) ? 1 : 0;
+    const uint32_t dw = yt - yb[i];
+    above = __funnelshift_l(dw, above, 1);
+    notbelow = __funnelshift_l(dw - 1u, notbelow, 1);
   }
+  const int cw = __popc(above), cc = __popc(notbelow) - cw;
   const int mine = cw | (cc << 16);
   const int incl = group_incl_scan<G>(mine);
   const int tot = __shfl_sync(FULL, incl, (lane & ~(G - 1)) + G - 1);
@@ -347,7 +361,7 @@ topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict_
   static_assert(FI >= 2 && NS >= 4 && CAP >= 128, "sift select: row too narrow / list too small for the winners' buffer");
   __shared__ __align__(16) uint2 s_list[4][CAP];             // per warp: survivors, later the winners (first 128)
   __shared__ __align__(16) uint2 s_cand[4][32];
-  __shared__ __align__(16) unsigned int s_hist[4][sift::SBINS];
+  __shared__ __align__(16) unsigned int s_hist[4][sift::SBINS + 4];        // + a spare word for empty slots
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + wib;
   if (r >= R) return;
@@ -377,13 +391,17 @@ topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict_
   for (int i = 0; i < NS; ++i) sv[i] = x[i * SSTR];
   float p;
   ok = sift::sample_pivot<G, NS>(ok, sv, s_hist[wib], jtarget, lane, p);
-  int cnt = 0;
+  uint32_t neg[4] = {0u, 0u, 0u, 0u};                        // four chains: E / 4 <= 16 sign bits each
 #pragma unroll
-  for (int e = 0; e < E; ++e) cnt += (x[e] >= p) ? 1 : 0;
+  for (int e = 0; e < E; ++e) sift::push_sign(neg[e & 3], x[e], p);
+  const int cnt = E - (__popc(neg[0]) + __popc(neg[1])) - (__popc(neg[2]) + __popc(neg[3]));
   const int incl = sift::group_incl_scan<G>(cnt);
   const int C = __shfl_sync(sift::FULL, incl, 31);
   ok = ok && C >= k && C <= CAP;
   if (ok) {                                                  // (warp-uniform)
+    // (the pivot again, through a shuffle ptxas cannot see through: with the same register in both passes it keeps the
+    //  counting pass's 28 predicates in a bit mask for this one -- two LOP3 per element there, an unpack here)
+    const float ps = __shfl_sync(sift::FULL, p, 0);
     uint32_t pos = (uint32_t)__cvta_generic_to_shared(list) + 8u * (uint32_t)(incl - cnt);
     const uint32_t nlane4 = ~((uint32_t)lane << 2);          // ~(4 lane + c) = ~(4 lane) - c
 #pragma unroll
@@ -396,7 +414,7 @@ topk_sift_kernel(Rows rows, int R, int W, int k, int jtarget, float *__restrict_
           "@q add.u32 %0, %0, 8;\n\t"
           "}\n"
           : "+r"(pos)
-          : "r"(nlane4 - (uint32_t)((e >> 2) * (4 * G) + (e & 3))), "f"(x[e]), "f"(p), "r"(__float_as_uint(x[e]))
+          : "r"(nlane4 - (uint32_t)((e >> 2) * (4 * G) + (e & 3))), "f"(x[e]), "f"(ps), "r"(__float_as_uint(x[e]))
           : "memory");
     }
   }
@@ -423,7 +441,7 @@ topk_sift_stream_kernel(Rows rows, int R, int W, int k, int jtarget, float *__re
   constexpr int SL = 16, CAP = 32 * SL, CH = 8;              // CH float4 per lane and chunk
   __shared__ __align__(16) uint2 s_list[4][CAP];
   __shared__ __align__(16) uint2 s_cand[4][32];
-  __shared__ __align__(16) unsigned int s_hist[4][sift::SBINS];
+  __shared__ __align__(16) unsigned int s_hist[4][sift::SBINS + 4];        // + a spare word for empty slots
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 4 + wib;
   if (r >= R) return;
@@ -467,14 +485,17 @@ topk_sift_stream_kernel(Rows rows, int R, int W, int k, int jtarget, float *__re
     int cnt = 0;
 #pragma unroll
     for (int e = 0; e + 1 < CH * 4; e += 2) mx = sift::max3_nan(mx, x[e], x[e + 1]);
+    uint32_t neg[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int e = 0; e < CH * 4; ++e) cnt += (x[e] >= p) ? 1 : 0;
+    for (int e = 0; e < CH * 4; ++e) sift::push_sign(neg[e & 3], x[e], p);
+    cnt = CH * 4 - (__popc(neg[0]) + __popc(neg[1])) - (__popc(neg[2]) + __popc(neg[3]));
     const int incl = sift::group_incl_scan<32>(cnt);
     const int tot = __shfl_sync(sift::FULL, incl, 31);
     if (C + tot > CAP) {                                     // (uniform) too many survivors: the marked-row pass
       ok = false;
       break;
     }
+    const float ps = __shfl_sync(sift::FULL, p, 0);          // (opaque copy: see topk_sift_kernel)
     uint32_t pos = (uint32_t)__cvta_generic_to_shared(list) + 8u * (uint32_t)(C + incl - cnt);
     const uint32_t nbase = ~((uint32_t)(t0 * 32 + lane) << 2);           // ~(4 (32 t0 + lane) + c) = nbase - c
 #pragma unroll
@@ -487,7 +508,7 @@ topk_sift_stream_kernel(Rows rows, int R, int W, int k, int jtarget, float *__re
           "@q add.u32 %0, %0, 8;\n\t"
           "}\n"
           : "+r"(pos)
-          : "r"(nbase - (uint32_t)((e >> 2) * 128 + (e & 3))), "f"(x[e]), "f"(p), "r"(__float_as_uint(x[e]))
+          : "r"(nbase - (uint32_t)((e >> 2) * 128 + (e & 3))), "f"(x[e]), "f"(ps), "r"(__float_as_uint(x[e]))
           : "memory");
     }
     C += tot;
