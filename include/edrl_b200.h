@@ -220,6 +220,54 @@ int edrl_gather_rows_fwd(const float *features, const int32_t *idx, int B, int T
 int edrl_gather_rows_bwd(const float *dout, const int32_t *idx, int B, int T, int D, int k,
                          float *dfeatures, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Next row -- DILR Barlow-Twins cross-correlation loss      code/fusion_net.py:656-677
+ *
+ * z1, z2 [B, D] fp32 (D = 2048 in the reference).  Replaces `c = bn1(z1).T @ bn2(z2); c.div_(4 batch_size)` and the
+ * four masked sums over the common block c[:dc, :dc] and the unique block c[dc:, dc:]; the D x D matrix is never
+ * stored.  BatchNorm1d(affine=False): training != 0 normalises with the batch statistics (biased variance, eps) and
+ * updates run_mean / run_var with `momentum` (unbiased variance), like nn.BatchNorm1d (code/fusion_net.py:653-654);
+ * training == 0 normalises with the running statistics.  out6 = (loss_c, on_diag_c, off_diag_c, loss_u, on_diag_u,
+ * off_diag_u), the reference's return tuple (:677).  The workspace keeps the normalised operands for the backward.
+ * ------------------------------------------------------------------------------------------ */
+size_t      edrl_dilr_workspace_bytes(int B, int D);
+int         edrl_dilr_bt_loss_fwd(const float *z1, const float *z2, int B, int D, int common_dim, int batch_size,
+                                  float eps, int training, float momentum, float *run_mean1, float *run_var1,
+                                  float *run_mean2, float *run_var2, float *out6, void *workspace,
+                                  size_t workspace_bytes, void *stream);
+/* grad_out6: upstream gradients of the six outputs (device); dz1 / dz2 [B, D] (either may be NULL). */
+int         edrl_dilr_bt_loss_bwd(int B, int D, int common_dim, int batch_size, int training, const float *grad_out6,
+                                  float *dz1, float *dz2, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Next row -- the loader's two views on the device             code/data_harvard.py:698-783
+ *
+ * x: `items` preprocessed samples of `per_item` values each -- fp32 in [0, 1], or uint8 (is_u8: the / 255 of :694-695
+ * is applied here).  low = clip(x, 0, 1) (the reference's zero-variance draw, :722-731), high = clip(x + N(0, sigma), 0, 1)
+ * (:769-783).  noise == NULL: the field comes from Philox4x32-10(seed, element index) + Box-Muller; shared_field != 0
+ * gives every item the same field, as the reference's per-item np.random.seed(seed_idx) does (:698).  noise != NULL:
+ * that tensor (already scaled, same shape as x) is added instead -- the parity mode.
+ * ------------------------------------------------------------------------------------------ */
+int         edrl_noise_views(const void *x, int is_u8, long long per_item, int items, float sigma,
+                             unsigned long long seed, int shared_field, const float *noise, float *low, float *high,
+                             void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Next row -- the small losses that close MedFusion.forward   code/fusion_net.py:929-942, 390-402
+ *
+ * pred [B, >= C] (row stride ldp; the reference slices pred[:, :2], :930), y int64 [B]: label-smoothed cross-entropy
+ * (:931-939).  mu_* / sig_* [B, Cm, F]: KL(N(mu, sigma) || N(0, 1)) as KL_between_normals / get_KL_loss compute it
+ * (summed over the class axis, averaged over batch and features).  out3 = (loss1, kl_fundus, kl_oct); one launch each
+ * way.  Gradient outputs may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int         edrl_head_losses_fwd(const float *pred, int ldp, const int64_t *y, int B, int C, float smoothing,
+                                 const float *mu_f, const float *sig_f, const float *mu_o, const float *sig_o, int Cm,
+                                 int F, float *out3, void *stream);
+int         edrl_head_losses_bwd(const float *pred, int ldp, const int64_t *y, int B, int C, float smoothing,
+                                 const float *mu_f, const float *sig_f, const float *mu_o, const float *sig_o, int Cm,
+                                 int F, const float *grad3, float *dpred, float *dmu_f, float *dsig_f, float *dmu_o,
+                                 float *dsig_o, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

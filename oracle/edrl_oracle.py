@@ -23,7 +23,7 @@ __all__ = [
     "gaussian_kernel", "mk_mmd", "mk_mmd_grad", "mmd_bandwidth",
     "eprl_sample_proxies", "eprl_scores", "eprl_scores_hoisted", "eprl_split",
     "topk_rows", "eprl_proxy_loss", "eprl_train_forward", "eprl_train_backward",
-    "eprl_eval_forward", "gather_rows", "select_gather",
+    "eprl_eval_forward", "gather_rows", "select_gather", "dilr_bt_loss_cross",
 ]
 
 
@@ -293,3 +293,57 @@ def gather_rows(features, idx):
 def select_gather(features, scores, k):
     vals, idx = topk_rows(scores, k)
     return gather_rows(features, idx), vals, idx
+
+
+# --------------------------------------------------------------------------
+# Next-row: DILR Barlow-Twins cross-correlation loss
+# --------------------------------------------------------------------------
+def dilr_bt_loss_cross(z1, z2, common_dim, batch_size, eps=1e-5, grad_w=None):
+    """code/fusion_net.py:656-677 with train-mode ``BatchNorm1d(affine=False)`` (batch mean, biased variance, eps).
+
+    c = bn1(z1).T @ bn2(z2) / (4 batch_size); over the common block c[:dc, :dc] and the unique block c[dc:, dc:]:
+    on-diagonal sum of (c_ii - 1)^2 (common) or c_ii^2 (unique), off-diagonal sum of c_ij^2, loss = on + 0.0051 off.
+    Returns the six values (loss_c, on_c, off_c, loss_u, on_u, off_u); with ``grad_w`` (six weights) also the gradients
+    of sum_k grad_w[k] out[k] w.r.t. z1 and z2 (closed form of what autograd does to the reference).
+    """
+    z1 = np.asarray(z1, dtype=np.float64)
+    z2 = np.asarray(z2, dtype=np.float64)
+    b, d = z1.shape
+    dc = int(common_dim)
+
+    def bn(z):
+        mean = z.mean(axis=0)
+        var = z.var(axis=0)                      # biased: what normalises in train mode
+        inv = 1.0 / np.sqrt(var + eps)
+        return (z - mean) * inv, inv
+
+    h1, inv1 = bn(z1)
+    h2, inv2 = bn(z2)
+    scale = 1.0 / (batch_size * 4)
+    c = (h1.T @ h2) * scale                                   # :658-661
+    cc, cu = c[:dc, :dc], c[dc:, dc:]
+    on_c = ((np.diag(cc) - 1.0) ** 2).sum()                   # :668
+    off_c = (cc ** 2).sum() - (np.diag(cc) ** 2).sum()        # :669
+    on_u = (np.diag(cu) ** 2).sum()                           # :671
+    off_u = (cu ** 2).sum() - (np.diag(cu) ** 2).sum()        # :672
+    out = np.array([on_c + 0.0051 * off_c, on_c, off_c, on_u + 0.0051 * off_u, on_u, off_u])
+    if grad_w is None:
+        return out
+    gw = np.asarray(grad_w, dtype=np.float64)
+    g_on_c, g_off_c = gw[0] + gw[1], 0.0051 * gw[0] + gw[2]
+    g_on_u, g_off_u = gw[3] + gw[4], 0.0051 * gw[3] + gw[5]
+    dcm = np.zeros_like(c)                                    # d total / d c
+    dcm[:dc, :dc] = 2.0 * g_off_c * cc
+    dcm[dc:, dc:] = 2.0 * g_off_u * cu
+    ii = np.arange(dc)
+    dcm[ii, ii] = 2.0 * g_on_c * (np.diag(cc) - 1.0)
+    jj = np.arange(dc, d)
+    dcm[jj, jj] = 2.0 * g_on_u * np.diag(cu)
+    dcm *= scale
+    dh1 = h2 @ dcm.T                                          # [b, d]
+    dh2 = h1 @ dcm
+
+    def bn_bwd(dh, h, inv):
+        return inv * (dh - dh.mean(axis=0) - h * (dh * h).mean(axis=0))
+
+    return out, bn_bwd(dh1, h1, inv1), bn_bwd(dh2, h2, inv2)

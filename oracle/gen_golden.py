@@ -192,12 +192,50 @@ def gen_eprl():
     np.savez_compressed(os.path.join(GOLD, "eprl_reference.npz"), **out)
 
 
+def gen_dilr():
+    """DILR.bt_loss_cross (code/fusion_net.py:656-677) of the unmodified reference, train-mode BatchNorm (batch statistics,
+    running-stat update), forward values and gradients w.r.t. both inputs of a weighted sum of the six outputs."""
+    import types
+    fn = ref_loader.load_reference_fusion_net()
+    out = {}
+    # name, B, D (BatchNorm width), common_dim, batch_size (the divisor's), seed
+    cases = [("tiny", 6, 16, 8, 6, 21), ("odd", 5, 24, 10, 8, 22), ("ref2048", 8, 2048, 1024, 8, 23)]
+    w = np.array([1.0, 0.3, -0.2, 0.7, 0.1, 0.5])
+    for (name, b, d, dc, bs, seed) in cases:
+        for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            torch.manual_seed(seed)
+            holder = types.SimpleNamespace(args=types.SimpleNamespace(batch_size=bs),
+                                           bn1=torch.nn.BatchNorm1d(d, affine=False).to(dtype),
+                                           bn2=torch.nn.BatchNorm1d(d, affine=False).to(dtype))
+            holder.bn1.train()
+            holder.bn2.train()
+            z1 = (torch.randn(b, d, dtype=dtype) * 1.5 + 0.3).requires_grad_(True)
+            z2 = (0.6 * z1.detach() + 0.8 * torch.randn(b, d, dtype=dtype) - 0.1).requires_grad_(True)
+            vals = fn.DILR.bt_loss_cross(holder, z1, z2, dc)          # the reference's own method on a stand-in self
+            total = sum(float(wi) * v for wi, v in zip(w, vals))
+            total.backward()
+            key = f"{name}_{tag}"
+            out[key + "_cfg"] = np.array([b, d, dc, bs, seed])
+            out[key + "_z1"] = z1.detach().numpy()
+            out[key + "_z2"] = z2.detach().numpy()
+            out[key + "_out"] = np.array([v.item() for v in vals])
+            out[key + "_dz1"] = z1.grad.numpy()
+            out[key + "_dz2"] = z2.grad.numpy()
+            out[key + "_rm1"] = holder.bn1.running_mean.numpy()
+            out[key + "_rv1"] = holder.bn1.running_var.numpy()
+            print(f"dilr {key} loss_c={vals[0].item():.8e} loss_u={vals[3].item():.8e}")
+    out["weights"] = w
+    np.savez_compressed(os.path.join(GOLD, "dilr_reference.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref_loader.reference_available():
         raise SystemExit("reference not mounted at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    gen_mmd()
-    gen_eprl()
+    if "--only-dilr" not in sys.argv:
+        gen_mmd()
+        gen_eprl()
+    gen_dilr()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)), "bytes")

@@ -63,6 +63,17 @@ PROTOTYPES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "edrl_gather_rows_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "edrl_gather_rows_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "edrl_noise_views": (c_int, [c_void_p, c_int, ctypes.c_longlong, c_int, c_float, ctypes.c_ulonglong, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    "edrl_head_losses_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_void_p, c_void_p]),
+    "edrl_head_losses_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "edrl_dilr_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "edrl_dilr_bt_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "edrl_dilr_bt_loss_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
 }
 
 ABI_VERSION = 1

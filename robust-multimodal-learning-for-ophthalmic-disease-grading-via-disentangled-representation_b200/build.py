@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libedrl_b200.so")
 STAMP = os.path.join(LIBDIR, "libedrl_b200.stamp")
-SOURCES = ["common.cu", "mmd.cu", "eprl.cu"]
+SOURCES = ["common.cu", "mmd.cu", "eprl.cu", "dilr.cu", "views.cu", "head.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "mmd_prep.cuh", "mmd_fwd.cuh", "mmd_bwd.cuh", "mmd_sweep.cuh", "topk_sift.cuh",
            os.path.join("..", "..", "include", "edrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -63,6 +63,11 @@ if _ref is not None:
         REFERENCE_EPRL = _ns["EPRL"]                       # the reference's own class, for A/B runs
         if os.environ.get("EDRL_SWAP_EPRL", "1") != "0":
             _ns["EPRL"] = _EPRL_B200                       # the classes' global scope: MedFusion.__init__ looks EPRL up here
+        if os.environ.get("EDRL_SWAP_DILR", os.environ.get("EDRL_SWAP_EPRL", "1")) != "0":
+            # the Barlow-Twins cross-correlation loss of DILR on the fused kernels (same method signature)
+            from edrl_b200.dilr import bt_loss_cross as _bt_loss_cross_b200
+            REFERENCE_BT_LOSS_CROSS = _ns["DILR"].bt_loss_cross
+            _ns["DILR"].bt_loss_cross = _bt_loss_cross_b200
         globals().update({k: v for k, v in _ns.items() if not k.startswith("__")})
         REFERENCE_LOADED = True
 
