@@ -440,6 +440,64 @@ def reference_driver_runs(steps=8):
     return out
 
 
+def next_rows_extras(peaks):
+    """the rows next to the path -- DILR Barlow-Twins loss (8f-1), device-side noise views (8f-3), fused head
+    losses + the whole stand-in step as one CUDA graph (8f-4) -- timed against the reference's torch op sequences."""
+    import importlib.util
+    import types
+    import edrl_b200
+    out = {}
+    try:
+        spec = importlib.util.spec_from_file_location("edrl_step_synthetic", os.path.join(ROOT, "examples", "edrl_step_synthetic.py"))
+        syn = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(syn)
+
+        def timeit(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return statistics.median(ts)
+
+        rows = []
+        for B in (32, 64, 256):
+            holder = types.SimpleNamespace(args=types.SimpleNamespace(batch_size=B),
+                                           bn1=torch.nn.BatchNorm1d(2048, affine=False).cuda(),
+                                           bn2=torch.nn.BatchNorm1d(2048, affine=False).cuda())
+            z1 = torch.randn(B, 2048, device="cuda")
+            z2 = 0.6 * z1 + 0.8 * torch.randn(B, 2048, device="cuda")
+
+            def run(fn):
+                a, b = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+                v = fn(holder, a, b, 1024)
+                ((v[0] + v[3]) / 2).backward()
+
+            ours = timeit(lambda: run(edrl_b200.bt_loss_cross))
+            ref = timeit(lambda: run(syn.torch_bt_loss_cross))
+            rows.append({"B": B, "D": 2048, "ours_ms": ours, "torch_eager_gpu_ms": ref, "speedup": ref / ours})
+        out["dilr_bt_loss_cross_fwd_bwd"] = {"rows": rows, "bound": "launch latency at the reference's batch sizes (4 kernels "
+                                             "against ~60 launches); fp32 CUDA cores, 2 x 1024^2 x B MACs each way"}
+        # noise views: batch 64 of the reference's shapes, HBM-bound (4 B read + 8 B written per element)
+        x = torch.rand(64, 1, 96, 96, 96, device="cuda")
+        ms = timeit(lambda: edrl_b200.noise_views(x, 0.5, 11), 10)
+        byts = x.numel() * 12
+        ref = timeit(lambda: (x.clamp(0, 1), (x + 0.5 * torch.randn_like(x)).clamp(0, 1)), 10)
+        out["noise_views_oct_batch64"] = {"ms": ms, "GB/s": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
+                                          "torch_eager_gpu_ms": ref, "bytes": byts,
+                                          "cpu_reference": "numpy on the loader's workers: ~20 ms per SAMPLE (reference_drivers)"}
+        out["synthetic_step_batch64"] = syn.compare(64, 10, "device")
+    except Exception as exc:
+        out["error"] = repr(exc)
+    return out
+
+
 def essence_path_vs_torch_gpu():
     """Essence-Point score + select + loss, forward + backward after the encoder, at the
     reference's shapes (C=2, S=800, F=256, k=100) against the reference's torch op sequence on the same GPU,
@@ -983,6 +1041,7 @@ def run_ours(args, rank, local_rank, world):
                 line["scale_anchor"] = {"error": repr(exc)}
             if not args.no_drivers:
                 line["reference_drivers"] = reference_driver_runs()
+            line["next_rows"] = next_rows_extras(peaks)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
