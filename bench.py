@@ -826,7 +826,7 @@ def run_ours(args, rank, local_rank, world):
                     "achieved": ach_f, "frac": ach_f / peak, "algorithmic_flops": flops_f}
         bwd_info = {"kernel": "mmd_bwd_pair_kernel (separate tile-recomputing backward)", "ms": b_ms,
                     "achieved": ach_b, "frac": ach_b / peak, "algorithmic_flops": flops_b}
-        if prec in ("tf32", "tf32h", "f16s"):
+        if prec in ("tf32", "tf32h", "f16s", "3xtf32") and not (prec == "3xtf32" and d > 768):
             # the training step's dominant launch: forward sums + gradient in one sweep over the Gram tiles
             g_ms = timed_steps(fused_only, reps, 2, flush, 1) / reps
             flops_g = flops_f + flops_b
@@ -836,7 +836,9 @@ def run_ours(args, rank, local_rank, world):
                 peak = flops_g / (flops_f / peak + flops_b / (2.0 * peak))
             elif prec == "f16s":
                 peak = peaks["bf16_burst"]            # both contractions issue kind::f16 MMAs
-            mode_id = {"tf32": 0, "tf32h": 1, "f16s": 2}[prec]
+            if prec == "3xtf32":
+                peak = peak / 3.0                     # three TF32 MMAs per product
+            mode_id = {"tf32": 0, "tf32h": 1, "f16s": 2, "3xtf32": 3}[prec]
             roof = {"bound": "tensor",
                     "kernel": (f"mmd_sweep_quad_kernel<FAST, MODE={mode_id}>" if d > 768 else f"mmd_sweep256_kernel<FAST, MODE={mode_id}>")
                               + " (forward sums + gradient, one persistent Gram sweep)",
@@ -850,7 +852,8 @@ def run_ours(args, rank, local_rank, world):
                         "tf32": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate)",
                         "tf32h": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s: Gram (1/3 of the work) at the "
                                  "TF32 rate (/2), G.Z (2/3) at the f16 rate",
-                        "f16s": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s (kind::f16 MMAs)"}[prec],
+                        "f16s": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s (kind::f16 MMAs)",
+                        "3xtf32": f"{peaks['source']} bf16 burst {peaks['bf16_burst']} TF/s / 2 (TF32 rate) / 3 (MMAs per product)"}[prec],
                     "algorithmic_flops": flops_g, "mma_per_product": 1,
                     "executed_tensor_flops": (2.0 * n * n * d * passes + 2.0 * n * n * d)}
         else:
@@ -975,8 +978,6 @@ def run_ours(args, rank, local_rank, world):
             # the same step in the other precision modes, same timing recipe
             def mode_roofline(o):
                 """fused C-ABI call (prep + sweep) alone in precision mode o: ms, achieved TFLOP/s, its own peak"""
-                if o == "3xtf32":
-                    return {}
                 fl = _flags(o)
                 ws_o = Workspace(N, N, d, fl, dev)
                 nn = 2 * N
@@ -993,7 +994,7 @@ def run_ours(args, rank, local_rank, world):
                 tf32_peak = peaks["bf16_burst"] / 2.0
                 fa = 3.0 * nn * nn * d
                 pk = {"tf32": tf32_peak, "tf32h": 3.0 / (1.0 / tf32_peak + 2.0 / peaks["bf16_burst"]),
-                      "f16s": peaks["bf16_burst"]}[o]
+                      "f16s": peaks["bf16_burst"], "3xtf32": tf32_peak / 3.0}[o]      # three TF32 MMAs per product
                 return {"fused_call_ms": t, "achieved_tflops": fa / (t * 1e-3) / 1e12, "peak_tflops": pk,
                         "frac": fa / (t * 1e-3) / 1e12 / pk}
 
@@ -1014,7 +1015,7 @@ def run_ours(args, rank, local_rank, world):
                 "binary16 with the same 11-bit significands (gradients agree with tf32 to 2e-5 |g|_inf). f16s: the Gram "
                 "too reads a scaled binary16 copy of the TF32-rounded operand (identical significands, exact products, "
                 "fp32 accumulation; agrees with tf32 to 2e-6 on the loss and 5e-5 |g|_inf on gradients). 3xtf32: hi/lo "
-                "split, fp32-level accuracy, first-generation kernels.")
+                "split, three MMAs per product, fp32-level accuracy, fused sweep (MODE 3) for d <= 768.")
             line["essence_path_vs_torch_gpu"] = essence_path_vs_torch_gpu()
             line["eval_missing_modality"] = eval_missing_modality()
             # the configs[3] workload (N = 65536 per side, d = 1024) on this one GPU through the same public API: the anchor

@@ -69,14 +69,16 @@ static Layout make_layout(int n_s, int n_t, int d, int flags) {
   L.off_fscale = o;   o += align_up((size_t)(L.d_pad + 1) * 4, 256);   // int[d_pad]: binary16 scale exponent per column; [d_pad]: of Z16
   o = align_up(o, 1024);
   size_t zbytes = align_up((size_t)L.n_pad * L.d_pad * 4, 1024);
+  // (3xTF32: Z_lo directly behind Z_hi and Z_lo^T directly behind Z_hi^T -- the fused sweep addresses each pair through
+  //  ONE tensor map of twice the rows)
   L.off_zhi = o;      o += zbytes;
-  L.off_zthi = o;     o += zbytes;
   L.off_zlo = o;      if (L.split3) o += zbytes;
+  L.off_zthi = o;     o += zbytes;
   L.off_ztlo = o;     if (L.split3) o += zbytes;
   L.off_zt16 = o;     if (L.h16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z^T [d_pad, n_pad]
   L.off_z16 = o;      if (L.s16) o += align_up((size_t)L.n_pad * L.d_pad * 2, 1024);   // binary16 Z [n_pad, d_pad]
   // fused sweep: row sums of G' per (512-column feature pass, column slab), float[passes][8][n_pad]
-  L.off_rowsum = o;   if (!L.split3) o += align_up((size_t)((L.d_pad + 511) / 512) * 8 * L.n_pad * 4, 1024);
+  L.off_rowsum = o;   o += align_up((size_t)((L.d_pad + 511) / 512) * 8 * L.n_pad * 4, 1024);
   L.total = o;
   return L;
 }
@@ -557,8 +559,9 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
                           size_t workspace_bytes, void *stream) {
   EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(X && Y && U, "MK_MMD forward_grad: null argument");
-  EDRL_CHECK_ARG((flags & EDRL_MMD_3XTF32) == 0, "MK_MMD forward_grad: the fused pass is TF32 / TF32H only");
   Layout L = make_layout(n_s, n_t, d, flags);
+  EDRL_CHECK_ARG(!L.split3 || L.d_pad <= P2_FEATS + P2_FEATS / 2,
+                 "MK_MMD forward_grad: the fused 3xTF32 pass covers d <= 768 (d = %d): use the separate kernels", d);
   if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n,
                  "MK_MMD forward_grad: row range [%d, %d) outside [0, %d)", row_begin, row_begin + row_count, L.n);
@@ -594,6 +597,16 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
                                  (size_t)((L.d_pad + 511) / 512) * SW_MAX_SPLIT * L.n_pad * sizeof(float), st));
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
+  if (L.split3) {
+    // 3xTF32: hi and lo parts behind one another -- rows [0, n_pad) of the S maps are Z_hi, [n_pad, 2 n_pad) Z_lo; rows
+    // [0, d_pad) of the P map are Z_hi^T, [d_pad, 2 d_pad) Z_lo^T
+    CUtensorMap tm3_z64, tm3_z128, tm3_zt;
+    if (int rc = make_tmap_2d_f32(&tm3_z64, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
+    if (int rc = make_tmap_2d_f32(&tm3_z128, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (int rc = make_tmap_2d_f32(&tm3_zt, ws + L.off_zthi, 2ull * L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
+    if (fast) return launch_sweep256_t<true, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
+    return launch_sweep256_t<false, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
+  }
   if (L.h16) {
     // binary16 (scaled) operands for G.Z; the Gram on TF32 (TF32H) or on the binary16 copy Z16 (F16S)
     CUtensorMap tm_z128, tm_zt16;
@@ -641,16 +654,17 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   const int rows = row_count + row_count2;
   const SweepPlan pl = make_plan(L, row_count, row_count2);
   const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  const float *zlo = L.split3 ? reinterpret_cast<const float *>(ws + L.off_zlo) : nullptr;
   const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool v4 = (d % 4 == 0) && ((((uintptr_t)U | (uintptr_t)dZ) & 15) == 0);
   dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
   if (v4)
-    mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
+    mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split, pl.pass_feats,
         reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   else
-    mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, cs, stats, grad_out, row_begin, row_count, row_begin2,
+    mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
                                                        row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split, pl.pass_feats,
         reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   EDRL_LAUNCHED();

@@ -20,16 +20,22 @@ constexpr int SW_MAX_SPLIT = 8;                // column slabs of a split virtua
 // MODE 0: TF32 everywhere.  1 (EDRL_MMD_TF32H): binary16 P phase.  2 (EDRL_MMD_F16S): the S phase too reads scaled
 // binary16 operands (Z16, kind::f16): a ring stage then holds 64 feature columns instead of 32.
 // The binary16 modes keep TWO G buffers (32 KiB each), so the epilogue of group g+1 overlaps the P phase of group g.
+// MODE 3 (EDRL_MMD_3XTF32): hi / lo split operands, three TF32 MMAs per product, fp32-level accuracy -- as ONE long
+// contraction each way.  S = Z_hi Z_hi^T + Z_lo Z_hi^T + Z_hi Z_lo^T is the TF32 Gram of [hi | lo | hi] against
+// [hi | hi | lo]: the K loop simply runs over three parts, the producer picking the hi or lo rows of the operand maps.
+// P the same over the column group: K atoms (Z_hi^T, G_hi), (Z_hi^T, G_lo), (Z_lo^T, G_hi); G is written as its TF32 hi
+// and lo parts (2 x 64 KiB), which leaves 5 ring stages instead of 9.
 template <int MODE>
 struct SweepCfg {
-  static constexpr bool H16 = MODE >= 1;
+  static constexpr bool H16 = MODE == 1 || MODE == 2;
   static constexpr bool S16 = MODE == 2;
+  static constexpr bool X3 = MODE == 3;
   static constexpr int S_COLS = S16 ? 64 : BK;                         // feature columns per 128-byte row of an S operand
-  static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : Q_G_BYTES;      // one G buffer: 64 rows x 256 columns
+  static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : (X3 ? 2 * Q_G_BYTES : Q_G_BYTES);   // one G buffer: 64 rows x 256 columns
   static constexpr int G_BUFS = H16 ? 2 : 1;
-  static constexpr int STAGES = 9;
+  static constexpr int STAGES = X3 ? 5 : 9;
   static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
-  static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : Q_GROUP / BK;     // K atoms (128-byte rows) per column group
+  static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : (X3 ? 3 * (Q_GROUP / BK) : Q_GROUP / BK);   // K atoms per column group
   static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
 };
 
@@ -54,7 +60,8 @@ struct SweepCtrl {
   float part[8][64];              // row-sum partials of an item (2 lane halves x 4 column chunks per row)
 };
 static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
-static_assert(SweepCfg<0>::SMEM_BYTES <= 232448 && SweepCfg<1>::SMEM_BYTES <= 232448, "smem budget");
+static_assert(SweepCfg<0>::SMEM_BYTES <= 232448 && SweepCfg<1>::SMEM_BYTES <= 232448 && SweepCfg<3>::SMEM_BYTES <= 232448,
+              "smem budget");
 
 // One work item of the sweep (make_plan): a 128-row panel x 512 feature columns, over the column groups
 // [g_begin, g_end) of 256 columns each; split panels write one partial output per slab.
@@ -106,6 +113,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   using Cfg = SweepCfg<MODE>;
   constexpr bool H16 = Cfg::H16;
   constexpr bool S16 = Cfg::S16;
+  constexpr bool X3 = Cfg::X3;
   constexpr int Q_STAGES = Cfg::STAGES;
   constexpr int GB = Cfg::G_BUFS;
   uint8_t *g_smem = smem;
@@ -118,7 +126,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const bool leader = (rank == 0);
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const int kchunks = S16 ? p.d_pad / 64 : p.kchunks;     // 128-byte K chunks of an S operand row; even
+  const int kch1 = S16 ? p.d_pad / 64 : p.kchunks;        // 128-byte K chunks of an S operand row; even
+  const int kchunks = X3 ? 3 * kch1 : kch1;                // 3xTF32: the parts [hi | lo | hi] x [hi | hi | lo] in one K loop
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (threadIdx.x == 0) {
@@ -176,18 +185,23 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       auto load_S = [&](int g) {
         const int jrow = (it.g_begin + g) * Q_GROUP + (int)rank * 128;
         for (int kc = 0; kc < kchunks; kc += 2) {
+          // 3xTF32: part 0 = hi x hi, 1 = lo x hi, 2 = hi x lo; the lo rows sit n_pad rows below the hi rows in both maps
+          const int part = X3 ? kc / kch1 : 0;
+          const int kk = kc - part * kch1;
+          const int ia = irow + ((X3 && part == 1) ? p.n_pad : 0);
+          const int jb = jrow + ((X3 && part == 2) ? p.n_pad : 0);
           {                                                   // two chunks of this CTA's 64 panel rows
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_z64, bar, kc * Cfg::S_COLS, irow);
-            tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * Cfg::S_COLS, irow);
+            tma_load_2d_pair_elect(st, &tm_z64, bar, kk * Cfg::S_COLS, ia);
+            tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kk + 1) * Cfg::S_COLS, ia);
             next();
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * Cfg::S_COLS, jrow);
+            tma_load_2d_pair_elect(st, &tm_z128, bar, (kk + h) * Cfg::S_COLS, jb);
             next();
           }
         }
@@ -197,8 +211,10 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_zt, bar, (it.g_begin + g) * Q_GROUP + a8 * Cfg::P_ATOM_COLS,
-                                   it.f0 + t * 256 + (int)rank * 128);
+            // 3xTF32: atoms 0-7 and 8-15 read Z_hi^T (against G_hi, G_lo), 16-23 Z_lo^T (d_pad rows below, against G_hi)
+            const int ac = X3 ? (a8 & 7) : a8;
+            const int fr = it.f0 + t * 256 + (int)rank * 128 + ((X3 && a8 >= 16) ? p.d_pad : 0);
+            tma_load_2d_pair_elect(st, &tm_zt, bar, (it.g_begin + g) * Q_GROUP + ac * Cfg::P_ATOM_COLS, fr);
             next();
           }
       };
@@ -270,7 +286,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
               mbar_wait(&ctl->full[s], ph);
               tc_fence_after();
               const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-              const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + a8 * P2_CHUNK);
+              // (3xTF32: G atoms 0-7 hold G_hi, 8-15 G_lo; K atoms 16-23 pair Z_lo^T with G_hi again)
+              const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + ((X3 && a8 >= 16) ? a8 - 16 : a8) * P2_CHUNK);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
                 const uint64_t adv = (uint64_t)(k * 2);
@@ -419,6 +436,10 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
                 const uint32_t pk = pack_half2(gv.x, gv.y);
                 gp[j >> 1] = pk;
                 rowsum = add_half2_f32(rowsum, pk);
+              } else if (X3) {
+                gp[j] = __float_as_uint(gv.x);               // fp32: split into TF32 hi + lo when it is written out
+                gp[j + 1] = __float_as_uint(gv.y);
+                rowsum += gv.x + gv.y;
               } else {
                 const float g0 = to_tf32(gv.x), g1 = to_tf32(gv.y);
                 gp[j] = __float_as_uint(g0);
@@ -443,6 +464,9 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
               const uint32_t hb = (uint32_t)__half_as_ushort(hv);
               if (j & 1) gp[j >> 1] |= hb << 16; else gp[j >> 1] = hb;
               rowsum += __half2float(hv);
+            } else if (X3) {
+              gp[j] = __float_as_uint(gv);
+              rowsum += gv;
             } else {
               const float g0 = to_tf32(gv);
               gp[j] = __float_as_uint(g0);
@@ -461,6 +485,23 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           for (int q4 = 0; q4 < 4; ++q4)
             *reinterpret_cast<uint4 *>(atom + (((cb + q4) ^ (r & 7)) << 4)) =
                 make_uint4(gp[q4 * 4 + 0], gp[q4 * 4 + 1], gp[q4 * 4 + 2], gp[q4 * 4 + 3]);
+        } else if (X3) {
+          // G = G_hi + G_lo (two TF32 numbers): the same atom layout twice, G_lo 64 KiB behind G_hi
+          uint8_t *atom = gbuf + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float hi4[4], lo4[4];
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float gvv = __uint_as_float(gp[q4 * 4 + c4]);
+              hi4[c4] = to_tf32(gvv);
+              lo4[c4] = to_tf32(gvv - hi4[c4]);
+            }
+            *reinterpret_cast<uint4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
+                make_uint4(__float_as_uint(hi4[0]), __float_as_uint(hi4[1]), __float_as_uint(hi4[2]), __float_as_uint(hi4[3]));
+            *reinterpret_cast<uint4 *>(atom + Q_G_BYTES + ((q4 ^ (r & 7)) << 4)) =
+                make_uint4(__float_as_uint(lo4[0]), __float_as_uint(lo4[1]), __float_as_uint(lo4[2]), __float_as_uint(lo4[3]));
+          }
         } else {
           uint8_t *atom = gbuf + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
@@ -1078,7 +1119,8 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
 // one block row per output row (no per-element division), 128-bit accesses when d % 4 == 0
 template <bool VEC4>
 __global__ void __launch_bounds__(128)
-mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const double *__restrict__ colsum_hi,
+mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ zlo,
+                      const double *__restrict__ colsum_hi,
                       const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
                       int row_begin2, int row_count2, int d, int d_pad, int n, int n_pad, int panels, int full_items,
                       int split, int pass_feats, const float *__restrict__ rowsum, float *__restrict__ dz) {
@@ -1107,7 +1149,11 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
         rs += rowsum[(size_t)(yp * 8 + sl) * n_pad + gr];
       }
       const float zc = fmaf(cv, fn, rs);                      // (rowsum(G')_i + c n) z_i
-      const float4 z = __ldg(reinterpret_cast<const float4 *>(zr + f));
+      float4 z = __ldg(reinterpret_cast<const float4 *>(zr + f));
+      if (zlo != nullptr) {                                   // 3xTF32: the operand is hi + lo
+        const float4 zl = __ldg(reinterpret_cast<const float4 *>(zlo + gr * d_pad + f));
+        z.x += zl.x; z.y += zl.y; z.z += zl.z; z.w += zl.w;
+      }
       float4 o;
       o.x = coef * (fmaf(zc, z.x, -cv * (float)colsum_hi[f + 0]) + u.x);
       o.y = coef * (fmaf(zc, z.y, -cv * (float)colsum_hi[f + 1]) + u.y);
@@ -1125,7 +1171,8 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
         u += ur[sl * slab + f];
         rs += rowsum[(size_t)(yp * 8 + sl) * n_pad + gr];
       }
-      dz[(size_t)r * d + f] = coef * (fmaf(fmaf(cv, fn, rs), __ldg(zr + f), -cv * (float)colsum_hi[f]) + u);
+      const float zv = __ldg(zr + f) + (zlo != nullptr ? __ldg(zlo + gr * d_pad + f) : 0.f);
+      dz[(size_t)r * d + f] = coef * (fmaf(fmaf(cv, fn, rs), zv, -cv * (float)colsum_hi[f]) + u);
     }
   }
 }

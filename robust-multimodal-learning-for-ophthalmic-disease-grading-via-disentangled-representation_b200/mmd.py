@@ -4,8 +4,9 @@
 ``MK_MMD(source, target, kernel_mul=2.0, kernel_num=5)`` is a ``torch.autograd.Function`` whose
 forward is one fused tcgen05 pass (the n x n kernel matrix never reaches HBM) and whose backward
 recomputes the kernel tiles.  Arithmetic: Gram on the tensor cores in TF32 (``"tf32"``) or as a
-hi/lo split with three MMAs per product (``"3xtf32"``, fp32-level accuracy); everything else fp32
-with fp64 block accumulators.
+hi/lo split with three MMAs per product (``"3xtf32"``, fp32-level accuracy; fused forward+gradient
+sweep for d <= 768, the separate first-generation kernels above); everything else fp32 with fp64
+block accumulators.
 """
 from __future__ import annotations
 
@@ -26,6 +27,12 @@ FLAG_F16S = 4
 # power-of-two scale for the whole matrix): identical significands and exact products, both contractions on kind::f16.
 _PRECISIONS = {"tf32": FLAG_TF32, "3xtf32": FLAG_3XTF32, "tf32h": FLAG_TF32H, "f16s": FLAG_F16S}
 _FUSED_FLAGS = (FLAG_TF32, FLAG_TF32H, FLAG_F16S)
+_FUSED_3X_MAX_D = 768      # the fused 3xTF32 sweep is the CTA-pair kernel (d_pad <= 768); wider inputs take the separate kernels
+
+
+def _fused(flags, d):
+    """Does a training step (gradients requested) of this precision and width take the fused forward+gradient sweep?"""
+    return _FUSED and (flags in _FUSED_FLAGS or (flags == FLAG_3XTF32 and d <= _FUSED_3X_MAX_D))
 _default_precision = os.environ.get("EDRL_MMD_PRECISION", "tf32").lower()
 NUM_STATS = 8
 # TF32 training steps use the fused pass (forward sums + gradient in one sweep over the Gram tiles);
@@ -102,7 +109,7 @@ class _MKMMDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x.device)
         ctx.U = None
-        if _FUSED and flags in _FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
+        if _fused(flags, d) and any(ctx.needs_input_grad[:2]):
             # one sweep over the Gram tiles: forward block sums + the bandwidth-independent gradient part U
             slabs = _grad_slabs(n_s, n_t, d, flags, n_s + n_t, 0, x.device.index)
             u = torch.empty(slabs, n_s + n_t, d, dtype=torch.float32, device=x.device)

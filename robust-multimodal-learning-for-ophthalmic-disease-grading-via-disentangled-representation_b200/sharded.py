@@ -95,7 +95,7 @@ class _ShardedMKMMDFunction(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=x_all.device)
         stats = torch.empty(NUM_STATS, dtype=torch.float32, device=x_all.device)
         ctx.U = None
-        if _mmd._FUSED and flags in _mmd._FUSED_FLAGS and any(ctx.needs_input_grad[:2]):
+        if _mmd._fused(flags, d) and any(ctx.needs_input_grad[:2]):
             # fused pass over this rank's rows (source rows, then target rows): partial sums + gradient part U
             (r0, c0), (r1, c1) = plan.source_rows(), plan.target_rows()
             slabs = _mmd._grad_slabs(plan.n_s, plan.n_t, d, flags, c0, c1, x_all.device.index)
