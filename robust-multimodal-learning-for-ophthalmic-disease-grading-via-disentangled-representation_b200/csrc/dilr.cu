@@ -189,18 +189,21 @@ corr_loss_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, i
   }
 }
 
-// ---- K3: backward through c.  grid (panels of 64 features over both blocks, 2 sides): side 0 computes dzh1^T for a panel
-// of z1 features (W zh2 over the block's column tiles), side 1 dzh2^T for a panel of z2 features (W^T zh1).  Per column tile
-// the correlation tile is recomputed, W = dL/dc goes to shared memory, then dzh^T[i, b] += sum_j W[i][j] zh_other^T[j, b]
-// for b in a chunk of BCH batch rows held in registers (BCH / 4 per thread); B > BCH repeats the tile loop per chunk.
+// ---- K3: backward through c.  grid (panels of 64 features over both blocks, 2 sides, JS column splits x batch chunks):
+// side 0 computes dzh1^T for a panel of z1 features (W zh2 over the block's column tiles), side 1 dzh2^T for a panel of z2
+// features (W^T zh1).  A block takes every JS-th column tile and one chunk of BCH batch rows: per tile the correlation tile
+// is recomputed, W = dL/dc goes to shared memory, then dzh^T[i, b] += sum_j W[i][j] zh_other^T[j, b] with the chunk's BCH / 4
+// batch columns per thread in registers.  Split js writes its own partial output (summed, in a fixed order, by K4).
 constexpr int BCH = 64;
+constexpr int JS = 4;
 __global__ void __launch_bounds__(256)
 corr_bwd_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, int D, int dc, int Bp, float scale,
-                const float *__restrict__ gout6, float *__restrict__ dzt1, float *__restrict__ dzt2) {
+                const float *__restrict__ gout6, float *__restrict__ dzt1, float *__restrict__ dzt2, size_t part_stride) {
   __shared__ __align__(16) float As[KC][TILE + 4], Bs[KC][TILE + 4];
   __shared__ float Ws[TILE][TILE + 1];
   __shared__ __align__(16) float Zs[TILE][BCH + 4];
   const int side = blockIdx.y;
+  const int js = blockIdx.z % JS, b0 = (blockIdx.z / JS) * BCH;
   const int pc = (dc + TILE - 1) / TILE;                     // panels of the common block come first
   const int blk = ((int)blockIdx.x >= pc) ? 1 : 0;
   const int f0 = blk ? dc : 0, nf = blk ? D - dc : dc;
@@ -208,69 +211,75 @@ corr_bwd_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, in
   if (i0 >= nf) return;
   const float *za = (side ? zt2 : zt1) + (size_t)f0 * Bp;    // this side's features (rows of the panel)
   const float *zb = (side ? zt1 : zt2) + (size_t)f0 * Bp;    // the other side's features (columns)
-  float *dz = (side ? dzt2 : dzt1) + (size_t)f0 * Bp;
+  float *dz = (side ? dzt2 : dzt1) + (size_t)js * part_stride + (size_t)f0 * Bp;
   const float g_loss = gout6[blk * 3 + 0], g_on = gout6[blk * 3 + 1], g_off = gout6[blk * 3 + 2];
   const float w_on = 2.f * (g_loss + g_on) * scale, w_off = 2.f * (OFF_W * g_loss + g_off) * scale;
   const float target = blk ? 0.f : 1.f;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int pi = tid >> 2, pb = (tid & 3) * (BCH / 4);       // P phase: row pi of the panel, batch columns pb .. pb + 15
-  for (int b0 = 0; b0 < Bp; b0 += BCH) {
-    float accp[BCH / 4];
+  float accp[BCH / 4];
 #pragma unroll
-    for (int q = 0; q < BCH / 4; ++q) accp[q] = 0.f;
-    for (int j0 = 0; j0 < nf; j0 += TILE) {
-      float c[4][4];
-      corr_tile(za, zb, i0, j0, nf, nf, Bp, As, Bs, c);      // c[u][v] = <za[i], zb[j]> (c is symmetric in the roles)
-      __syncthreads();
+  for (int q = 0; q < BCH / 4; ++q) accp[q] = 0.f;
+  for (int j0 = js * TILE; j0 < nf; j0 += JS * TILE) {
+    float c[4][4];
+    corr_tile(za, zb, i0, j0, nf, nf, Bp, As, Bs, c);        // c[u][v] = <za[i], zb[j]> (c is symmetric in the roles)
+    __syncthreads();
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int i = i0 + 4 * ty + u, j = j0 + 4 * tx + v;
-          const float cv = c[u][v] * scale;
-          float w = 0.f;
-          if (i < nf && j < nf) w = (i == j) ? w_on * (cv - target) : w_off * cv;
-          Ws[4 * ty + u][4 * tx + v] = w;
-        }
-      // the other side's normalised rows for this column tile and batch chunk
-      for (int t = tid; t < TILE * (BCH / 4); t += 256) {
-        const int jj = t / (BCH / 4), b4 = (t % (BCH / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j0 + jj < nf && b0 + b4 < Bp) v = *reinterpret_cast<const float4 *>(zb + (size_t)(j0 + jj) * Bp + b0 + b4);
-        *reinterpret_cast<float4 *>(&Zs[jj][b4]) = v;
+      for (int v = 0; v < 4; ++v) {
+        const int i = i0 + 4 * ty + u, j = j0 + 4 * tx + v;
+        const float cv = c[u][v] * scale;
+        float w = 0.f;
+        if (i < nf && j < nf) w = (i == j) ? w_on * (cv - target) : w_off * cv;
+        Ws[4 * ty + u][4 * tx + v] = w;
       }
-      __syncthreads();
-#pragma unroll 4
-      for (int jj = 0; jj < TILE; ++jj) {
-        const float w = Ws[pi][jj];
-#pragma unroll
-        for (int q = 0; q < BCH / 4; q += 4) {
-          const float4 zv = *reinterpret_cast<const float4 *>(&Zs[jj][pb + q]);
-          accp[q + 0] = fmaf(w, zv.x, accp[q + 0]);
-          accp[q + 1] = fmaf(w, zv.y, accp[q + 1]);
-          accp[q + 2] = fmaf(w, zv.z, accp[q + 2]);
-          accp[q + 3] = fmaf(w, zv.w, accp[q + 3]);
-        }
-      }
-      __syncthreads();
+    // the other side's normalised rows for this column tile and batch chunk
+    for (int t = tid; t < TILE * (BCH / 4); t += 256) {
+      const int jj = t / (BCH / 4), b4 = (t % (BCH / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + jj < nf && b0 + b4 < Bp) v = *reinterpret_cast<const float4 *>(zb + (size_t)(j0 + jj) * Bp + b0 + b4);
+      *reinterpret_cast<float4 *>(&Zs[jj][b4]) = v;
     }
-    if (i0 + pi < nf) {
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < TILE; ++jj) {
+      const float w = Ws[pi][jj];
 #pragma unroll
       for (int q = 0; q < BCH / 4; q += 4) {
-        if (b0 + pb + q < Bp)
-          *reinterpret_cast<float4 *>(dz + (size_t)(i0 + pi) * Bp + b0 + pb + q) =
-              make_float4(accp[q], accp[q + 1], accp[q + 2], accp[q + 3]);
+        const float4 zv = *reinterpret_cast<const float4 *>(&Zs[jj][pb + q]);
+        accp[q + 0] = fmaf(w, zv.x, accp[q + 0]);
+        accp[q + 1] = fmaf(w, zv.y, accp[q + 1]);
+        accp[q + 2] = fmaf(w, zv.z, accp[q + 2]);
+        accp[q + 3] = fmaf(w, zv.w, accp[q + 3]);
       }
     }
+    __syncthreads();
   }
+  if (i0 + pi < nf) {
+#pragma unroll
+    for (int q = 0; q < BCH / 4; q += 4) {
+      if (b0 + pb + q < Bp)
+        *reinterpret_cast<float4 *>(dz + (size_t)(i0 + pi) * Bp + b0 + pb + q) =
+            make_float4(accp[q], accp[q + 1], accp[q + 2], accp[q + 3]);
+    }
+  }
+}
+
+// d zh^T element: the JS column-split partials of K3, added in a fixed order
+__device__ __forceinline__ float dzh(const float *__restrict__ dzt, size_t part_stride, size_t o) {
+  float g = dzt[o];
+#pragma unroll
+  for (int p = 1; p < JS; ++p) g += dzt[(size_t)p * part_stride + o];
+  return g;
 }
 
 // ---- K4: BatchNorm backward (train: dz = inv (dzh - mean_b dzh - zh mean_b(dzh zh)); eval: dz = inv dzh), back to [B, D].
 // grid (ceil(D / 32), 2), 256 threads: lane = feature, the 8 warps split the batch rows.
 __global__ void __launch_bounds__(256)
 bn_bwd_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, const float *__restrict__ dzt1,
-              const float *__restrict__ dzt2, const float *__restrict__ stats, int B, int D, int Bp, int training,
-              float *__restrict__ dz1, float *__restrict__ dz2) {
+              const float *__restrict__ dzt2, size_t part_stride, const float *__restrict__ stats, int B, int D, int Bp,
+              int training, float *__restrict__ dz1, float *__restrict__ dz2) {
   __shared__ float s_a[8][32], s_b[8][32];
   const int which = blockIdx.y;
   const float *zt = which ? zt2 : zt1, *dzt = which ? dzt2 : dzt1;
@@ -283,7 +292,7 @@ bn_bwd_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, cons
     float a = 0.f, b = 0.f;
     if (j < D)
       for (int r = warp; r < B; r += 8) {
-        const float g = dzt[(size_t)j * Bp + r];
+        const float g = dzh(dzt, part_stride, (size_t)j * Bp + r);
         a += g;
         b = fmaf(g, zt[(size_t)j * Bp + r], b);
       }
@@ -303,7 +312,7 @@ bn_bwd_kernel(const float *__restrict__ zt1, const float *__restrict__ zt2, cons
   if (j < D) {
     const float inv = stats[(size_t)which * 2 * D + D + j];
     for (int r = warp; r < B; r += 8)
-      dz[(size_t)r * D + j] = inv * (dzt[(size_t)j * Bp + r] - m1 - zt[(size_t)j * Bp + r] * m2);
+      dz[(size_t)r * D + j] = inv * (dzh(dzt, part_stride, (size_t)j * Bp + r) - m1 - zt[(size_t)j * Bp + r] * m2);
   }
 }
 
@@ -318,14 +327,15 @@ extern "C" {
 size_t edrl_dilr_workspace_bytes(int B, int D) {
   if (B <= 0 || D <= 0) return 0;
   const size_t Bp = align_up((size_t)B, 64);
-  // [acc f64[4] | ticket | pad -> 256 B | stats f32[4 D] | zt1, zt2, dzt1, dzt2 f32[D, Bp] each]
-  return 256 + align_up((size_t)4 * D * 4, 256) + 4 * align_up((size_t)D * Bp * 4, 256);
+  // [acc f64[4] | ticket | pad -> 256 B | stats f32[4 D] | zt1, zt2 f32[D, Bp] | dzt1, dzt2 f32[JS][D, Bp]]
+  return 256 + align_up((size_t)4 * D * 4, 256) + (size_t)(2 + 2 * dilr::JS) * align_up((size_t)D * Bp * 4, 256);
 }
 
 struct DilrWs {
   double *acc;
   unsigned *ticket;
   float *stats, *zt1, *zt2, *dzt1, *dzt2;
+  size_t part_stride;        // floats between the JS partial copies of a dzt array
   int Bp;
 };
 static DilrWs dilr_ws(void *ws, int B, int D) {
@@ -341,7 +351,8 @@ static DilrWs dilr_ws(void *ws, int B, int D) {
   w.zt1 = reinterpret_cast<float *>(p);
   w.zt2 = reinterpret_cast<float *>(p + m);
   w.dzt1 = reinterpret_cast<float *>(p + 2 * m);
-  w.dzt2 = reinterpret_cast<float *>(p + 3 * m);
+  w.dzt2 = reinterpret_cast<float *>(p + (2 + JS) * m);
+  w.part_stride = m / 4;
   return w;
 }
 
@@ -378,11 +389,12 @@ int edrl_dilr_bt_loss_bwd(int B, int D, int common_dim, int batch_size, int trai
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const DilrWs w = dilr_ws(workspace, B, D);
   const int panels = (common_dim + TILE - 1) / TILE + (D - common_dim + TILE - 1) / TILE;
-  corr_bwd_kernel<<<dim3(panels, 2), 256, 0, st>>>(w.zt1, w.zt2, D, common_dim, w.Bp, 1.0f / (4.0f * (float)batch_size),
-                                                   grad_out6, w.dzt1, w.dzt2);
+  corr_bwd_kernel<<<dim3(panels, 2, JS * (w.Bp / BCH)), 256, 0, st>>>(w.zt1, w.zt2, D, common_dim, w.Bp,
+                                                                      1.0f / (4.0f * (float)batch_size), grad_out6, w.dzt1,
+                                                                      w.dzt2, w.part_stride);
   EDRL_LAUNCHED();
-  bn_bwd_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(w.zt1, w.zt2, w.dzt1, w.dzt2, w.stats, B, D, w.Bp, training, dz1,
-                                                        dz2);
+  bn_bwd_kernel<<<dim3((D + 31) / 32, 2), 256, 0, st>>>(w.zt1, w.zt2, w.dzt1, w.dzt2, w.part_stride, w.stats, B, D, w.Bp,
+                                                        training, dz1, dz2);
   EDRL_LAUNCHED();
   return 0;
 }

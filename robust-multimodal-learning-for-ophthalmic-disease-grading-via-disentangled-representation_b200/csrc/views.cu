@@ -55,6 +55,7 @@ noise_views_kernel(const void *__restrict__ xin, long long per_item, int items, 
                    float *__restrict__ high) {
   const long long total4 = (per_item * items + 3) / 4;
   const long long total = per_item * items;
+#pragma unroll 2                                             // (two independent quads in flight per thread)
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4;
        q += (long long)gridDim.x * blockDim.x) {
     const long long e0 = q * 4;
@@ -145,7 +146,7 @@ int edrl_noise_views(const void *x, int is_u8, long long per_item, int items, fl
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
   long long blocks = (total4 + 255) / 256;
-  const long long cap = (long long)sms * 16;
+  const long long cap = (long long)sms * 32;
   if (blocks > cap) blocks = cap;
   if (is_u8)
     views::noise_views_kernel<true><<<(int)blocks, 256, 0, st>>>(x, per_item, items, sigma, seed, shared_field, noise, low, high);

@@ -55,7 +55,7 @@ def test_bench_reference_arm_contract():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1"], capture_output=True, text=True, timeout=600,
+                          "--warmup", "1", "--ref-budget-s", "1"], capture_output=True, text=True, timeout=600,
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
@@ -66,5 +66,8 @@ def test_bench_reference_arm_contract():
         assert key in j, key
     assert j["impl"] == "reference" and j["unit"] == "samples/s" and j["higher_is_better"] is True
     assert j["config"]["N_per_side"] == 8192 and j["config"]["d"] == 512 and j["vs_baseline"] is None
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
+    # the reference's own MMD.py from the oracle/_ref copy when build() made one, else the torch port; whole steps
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1 and j["value"] > 0
+    assert j["steps_measured"] == 1 and j["extrapolated"] is False
+    assert set(j["config"]) == {"workload", "N_per_side", "d", "kernel_mul", "kernel_num", "parallelism", "step"}
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
