@@ -1844,7 +1844,10 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
   static const bool novec = (getenv("EDRL_TOPK_VEC") != nullptr && atoi(getenv("EDRL_TOPK_VEC")) == 0);
   static const bool nosift = (getenv("EDRL_TOPK_SIFT") != nullptr && atoi(getenv("EDRL_TOPK_SIFT")) == 0);
-  if (uniform && Wmax >= 512 && Wmax <= 2048 && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
+  // rows from this width on take the streaming sift kernel (80 registers, 6 blocks per SM) instead of the resident one,
+  // whose row in registers costs occupancy from W = 1600 on (128 registers, 4 blocks per SM)
+  static const int stream_minw = getenv("EDRL_TOPK_STREAM_MINW") ? atoi(getenv("EDRL_TOPK_STREAM_MINW")) : 2049;
+  if (uniform && Wmax >= 512 && Wmax <= 2048 && Wmax < stream_minw && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
     // sift select (topk_sift.cuh): sample pivot -> survivors -> exact select, when the sampling plan fits the list
     const int W4 = Wmax >> 2;
     bool done = false;
@@ -1890,7 +1893,8 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
       return 0;
     }
   }
-  if (uniform && Wmax > 2048 && Wmax <= 8192 && k <= 128 && !legacy && !novec && rows.vec4_ok()) {
+  if (uniform && ((Wmax > 2048 && Wmax <= 8192) || (Wmax >= 1024 && Wmax >= stream_minw && Wmax <= 2048 && !nosift)) && k <= 128 &&
+      !legacy && !novec && rows.vec4_ok()) {
     // wide rows.  Streaming sift select, one warp per row, when the sampling plan fits (1024 sample elements, 512
     // list entries); the rows it marks -- or, without it, all rows -- go to one 256-thread block per row with the row
     // in registers (4 or 8 float4 per thread)
@@ -1908,15 +1912,19 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
     int sms = device_sm_count();
     if (sms <= 0) sms = 148;
     const int grid = marked ? (R < 4 * sms ? R : 4 * sms) : R;
-    if (Wmax <= 4096) {
+    if (!marked && Wmax <= 2048) {
+      // (no sampling plan for this (W, k): rows this narrow go on to the warp-per-row kernels below)
+    } else if (Wmax <= 4096) {
       if (sorted) topk_vecblock_kernel<4, true, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
       else topk_vecblock_kernel<4, false, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
     } else {
       if (sorted) topk_vecblock_kernel<8, true, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
       else topk_vecblock_kernel<8, false, Rows><<<grid, VB_THREADS, 0, st>>>(rows, R, Wmax, k, vals, idx, marked);
     }
-    EDRL_LAUNCHED();
-    return 0;
+    if (marked || Wmax > 2048) {
+      EDRL_LAUNCHED();
+      return 0;
+    }
   }
   if (Wmax <= 2048 && k <= 128 && !legacy) {
     const bool full = uniform && (Wmax % 32 == 0);

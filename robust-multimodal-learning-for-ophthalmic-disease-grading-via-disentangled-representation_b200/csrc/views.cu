@@ -40,9 +40,11 @@ __device__ __forceinline__ void normals4(const uint32_t (&w)[4], float (&n)[4]) 
   for (int p = 0; p < 2; ++p) {
     const float u1 = ((float)w[2 * p] + 1.0f) * 2.3283064365386963e-10f;        // (0, 1]
     const float u2 = (float)w[2 * p + 1] * 2.3283064365386963e-10f;             // [0, 1)
-    const float rad = sqrtf(-2.0f * logf(u1));
+    // (MUFU lg2 / sin / cos: the kernel is otherwise bound by the transcendental sequences, not by HBM; a noise field
+    //  does not need the last two bits of a logarithm)
+    const float rad = sqrtf(-2.0f * __logf(u1));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    __sincosf(6.283185307179586f * u2, &s, &c);
     n[2 * p] = rad * c;
     n[2 * p + 1] = rad * s;
   }
