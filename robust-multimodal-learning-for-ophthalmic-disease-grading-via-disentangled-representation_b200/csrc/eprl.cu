@@ -1001,13 +1001,16 @@ __device__ __forceinline__ void emit_winners(uint2 *buf, int k, int lane, uint32
     }
     }
   } else {
+    // (row pointers advanced by the lane once, the four strides as immediates)
+    float *vp = vrow + lane;
+    int *ip = irow + lane;
+    const uint2 *bp = buf + lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int t2 = lane + 32 * i;
-      if (t2 < k) {
-        const uint2 cc = buf[t2];
-        vrow[t2] = __uint_as_float(cc.y);
-        irow[t2] = (int)~cc.x;
+      if (lane + 32 * i < k) {
+        const uint2 cc = bp[32 * i];
+        vp[32 * i] = __uint_as_float(cc.y);
+        ip[32 * i] = (int)~cc.x;
       }
     }
   }

@@ -162,6 +162,24 @@ __device__ __forceinline__ bool walk_from_top(const unsigned int *hist, int need
 #pragma unroll
   for (int i = 0; i < BPL; ++i) t += c[i];
   const int incl = group_incl_scan<G>(t);
+  if (BPL == 2) {
+    // branch-free: every lane works out the answer of its own two bins, the one lane whose range [excl, incl) holds
+    // position need - 1 publishes it
+    const int excl = incl - t;
+    const bool mine = excl < need && incl >= need;
+    const uint32_t hit = group_ballot<G>(mine, lane);
+    const int want = need - excl;                            // wanted from this lane's two bins
+    const bool first = c[0] >= want;
+    const int bn = 2 * (G - 1 - gl) + (first ? 1 : 0);
+    const int cb = first ? c[0] : c[1];
+    const int rm = first ? want : want - c[0];
+    const int pk = bn | (cb << 8) | (rm << 20);
+    const int got = __shfl_sync(FULL, pk, (__ffs(hit | 0x80000000u) - 1 + (lane & ~(G - 1))) & 31);
+    bin = got & 255;
+    cntb = (got >> 8) & 4095;
+    rem = got >> 20;
+    return hit != 0u;
+  }
   const uint32_t hit = group_ballot<G>(incl >= need, lane);
   const int L = __ffs(hit) - 1;                              // -1: no lane reaches `need`
   int packed = 0;                                            // bin | cntb << 8 | rem << 20
@@ -288,11 +306,18 @@ __device__ __forceinline__ bool select_survivors(bool active, uint2 *list, uint2
 #pragma unroll 4
   for (int j = 0; j < cn; ++j) {
     const uint2 o = cand[j];
-    const float ov = __uint_as_float(o.y);
 #pragma unroll
     for (int q = 0; q < CPL; ++q) {
-      const float cv = __uint_as_float(me[q].y);
-      rank[q] += (ov > cv || (ov == cv && o.x > me[q].x)) ? 1 : 0;       // .x = ~index: larger = lower index = earlier
+      // rank += (ov > cv) || (ov == cv && o.x > me.x)   (.x = ~index: larger = lower index = earlier), without branches
+      asm("{\n\t"
+          ".reg .pred a, b;\n\t"
+          "setp.eq.f32 b, %1, %2;\n\t"
+          "setp.gt.and.u32 b, %3, %4, b;\n\t"
+          "setp.gt.or.f32 a, %1, %2, b;\n\t"
+          "@a add.s32 %0, %0, 1;\n\t"
+          "}\n"
+          : "+r"(rank[q])
+          : "f"(__uint_as_float(o.y)), "f"(__uint_as_float(me[q].y)), "r"(o.x), "r"(me[q].x));
     }
   }
   float tv = __int_as_float(0xff800000);
