@@ -1001,9 +1001,11 @@ __device__ __forceinline__ void emit_winners(uint2 *buf, int k, int lane, uint32
     }
     }
   } else {
-    // (row pointers advanced by the lane once, the four strides as immediates)
+    // (row pointers advanced by the lane ONCE and made opaque: otherwise the compiler rebuilds both 64-bit addresses
+    //  inside each of the four predicated stores, 16 instructions a piece)
     float *vp = vrow + lane;
     int *ip = irow + lane;
+    asm volatile("" : "+l"(vp), "+l"(ip));
     const uint2 *bp = buf + lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -1829,7 +1831,7 @@ static SiftPlan sift_plan(int W, int k, int m_samples, int cap) {
     mu = k + z * sigma;
   }
   const double q = mu / W;
-  const double upper = mu + z * sigma + 0.15 * mu;           // (a 64-bin histogram of a bell-shaped row: <= ~0.15 mu per bin)
+  const double upper = mu + z * sigma + 0.125 * mu;          // (+ the pivot's own bin: 61 bins over ~5.6 sigma of a bell-shaped sample)
   SiftPlan p;
   p.ok = upper <= cap && q < 0.5;
   p.jtarget = (int)ceil(q * m);
@@ -1867,7 +1869,7 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
     }                                                                                                                 \
   }
     EDRL_SIFT_CASE(4, false, 1, 8)       // W = 512
-    EDRL_SIFT_CASE(6, true, 2, 8)        // W = 800 (the reference's S)
+    EDRL_SIFT_CASE(6, true, 3, 8)        // W = 800 (the reference's S): 8 sample values per lane
     EDRL_SIFT_CASE(8, false, 2, 8)       // W = 1024
     EDRL_SIFT_CASE(12, true, 2, 8)       // W = 1600 (C = 3 negatives)
     EDRL_SIFT_CASE(16, false, 2, 8)      // W = 2048
