@@ -394,12 +394,18 @@ static int quad_clusters_resident() {
   return cached;
 }
 
-static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int sms_override = 0) {
-  SweepPlan pl;
-  pl.panels = (row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM;
+static bool quad_wanted(const Layout &L) {
   static const bool no_quad = (getenv("EDRL_MMD_QUAD") != nullptr && atoi(getenv("EDRL_MMD_QUAD")) == 0);   // A/B runs
   // (up to 768 columns the second pair would hold one 256-column tile or less: two pair passes are faster)
-  pl.quad = (L.d_pad > P2_FEATS + P2_FEATS / 2 && !no_quad) ? 1 : 0;
+  return L.d_pad > P2_FEATS + P2_FEATS / 2 && !no_quad;
+}
+
+// force_kind: -1 = by width, 0 = pair kernel, 1 = quad kernel; clusters_override: persistent clusters available (hybrid)
+static SweepPlan make_plan_panels(const Layout &L, int panels, int sms_override = 0, int force_kind = -1,
+                                  int clusters_override = 0) {
+  SweepPlan pl;
+  pl.panels = panels;
+  pl.quad = (force_kind < 0 ? quad_wanted(L) : force_kind != 0) ? 1 : 0;
   pl.pass_feats = pl.quad ? 2 * P2_FEATS : P2_FEATS;
   const int ny = (L.d_pad + pl.pass_feats - 1) / pl.pass_feats;
   pl.vpanels = pl.panels * ny;
@@ -413,6 +419,7 @@ static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int s
     const int fit = quad_clusters_resident();
     if (fit > 0 && fit < C) C = fit;
   }
+  if (clusters_override > 0) C = clusters_override;
   const int nG = L.n_pad / Q_GROUP;
   pl.full_items = (pl.vpanels / C) * C;
   const int R = pl.vpanels - pl.full_items;
@@ -433,6 +440,75 @@ static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int s
   pl.items = pl.full_items + (pl.vpanels - pl.full_items) * pl.split;
   pl.pairs = pl.items < C ? pl.items : C;
   return pl;
+}
+
+static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int sms_override = 0) {
+  return make_plan_panels(L, (row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM, sms_override);
+}
+
+// A second stream for one call: `side` runs concurrently with the caller's stream between fork() and join().  One side
+// stream and two events per device, created on first use (event record / wait only: legal under stream capture, where
+// they fork and join the captured graph).
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int fork(cudaStream_t main) {
+    static cudaStream_t s_side[16] = {};
+    static cudaEvent_t s_ev[16][2] = {};
+    int dev = 0;
+    EDRL_CUDA_OK(cudaGetDevice(&dev));
+    EDRL_CHECK_ARG(dev >= 0 && dev < 16, "MK_MMD: device index %d not supported by the hybrid launch", dev);
+    if (s_side[dev] == nullptr) {
+      EDRL_CUDA_OK(cudaStreamCreateWithFlags(&s_side[dev], cudaStreamNonBlocking));
+      EDRL_CUDA_OK(cudaEventCreateWithFlags(&s_ev[dev][0], cudaEventDisableTiming));
+      EDRL_CUDA_OK(cudaEventCreateWithFlags(&s_ev[dev][1], cudaEventDisableTiming));
+    }
+    side = s_side[dev];
+    ev_fork = s_ev[dev][0];
+    ev_join = s_ev[dev][1];
+    EDRL_CUDA_OK(cudaEventRecord(ev_fork, main));
+    EDRL_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0));
+    return 0;
+  }
+  int join(cudaStream_t main) {
+    EDRL_CUDA_OK(cudaEventRecord(ev_join, side));
+    EDRL_CUDA_OK(cudaStreamWaitEvent(main, ev_join, 0));
+    return 0;
+  }
+};
+
+// Hybrid launch for d > 768: 4-CTA clusters must sit inside one GPC, so only 33 of them are resident on 148 SMs and 16
+// SMs would idle through the whole sweep.  The quad kernel takes the first panels, a PAIR kernel (two 512-column feature
+// passes per panel, concurrently on a forked stream) the last ones, in the ratio of their measured speeds: a pair needs
+// ny (d_pad + 512) per panel where a cluster needs ny_q (d_pad / 2 + 512) (S + P columns streamed; x 0.88 measured at
+// d = 1024: 11.1 ms against 4.2 ms per panel at n = 131072).
+struct HybridPlan {
+  bool on;
+  SweepPlan q, pr;     // quad part: panels [0, q.panels); pair part: panels [q.panels, q.panels + pr.panels)
+};
+static HybridPlan make_hybrid(const Layout &L, int row_count, int row_count2) {
+  HybridPlan h;
+  h.on = false;
+  h.q = make_plan(L, row_count, row_count2);
+  h.pr = h.q;
+  static const int mode = getenv("EDRL_MMD_HYBRID") ? atoi(getenv("EDRL_MMD_HYBRID")) : 1;   // 0 off, 1 auto, 2 force (tests)
+  if (!h.q.quad || mode == 0 || L.h16 || L.split3) return h;     // (the TF32 sweep only: tf32h / f16s keep one launch)
+  int sms = device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int cq = quad_clusters_resident();
+  const int cp = (sms - 4 * cq) / 2;
+  if (cq <= 0 || cp <= 0) return h;
+  const int P = h.q.panels;
+  const int ny_p = (L.d_pad + P2_FEATS - 1) / P2_FEATS, ny_q = (L.d_pad + 2 * P2_FEATS - 1) / (2 * P2_FEATS);
+  static const double kr = getenv("EDRL_MMD_HYBRID_RATIO") ? atof(getenv("EDRL_MMD_HYBRID_RATIO")) : 0.88;   // A/B runs
+  const double ratio = kr * (double)ny_p * (L.d_pad + 512.0) / ((double)ny_q * (L.d_pad / 2.0 + 512.0));
+  int pp = (int)((double)P * (cp / ratio) / (cq + cp / ratio));
+  if (mode == 2 && pp < 1 && P >= 2) pp = 1;
+  if (pp < (mode == 2 ? 1 : cp) || pp >= P) return h;        // too few panels to keep the idle SMs busy for the whole sweep
+  h.on = true;
+  h.q = make_plan_panels(L, P - pp, 0, 1);
+  h.pr = make_plan_panels(L, pp, 0, 0, cp);
+  return h;
 }
 
 
@@ -512,6 +588,7 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
   p.acc = nullptr; p.ticket = nullptr; p.partial = nullptr; p.loss = nullptr; p.stats_out = nullptr;
   p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0; p.fscale = nullptr;
+  p.panel0 = 0; p.ticket_total = 0;
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
   if (!L.split3 && !legacy) {
@@ -541,7 +618,8 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
 
 int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2) {
   if (n_s <= 0 || n_t <= 0 || d <= 0 || row_count <= 0 || row_count2 < 0) return 1;
-  return make_plan(make_layout(n_s, n_t, d, flags), row_count, row_count2).split;
+  const HybridPlan h = make_hybrid(make_layout(n_s, n_t, d, flags), row_count, row_count2);
+  return (h.on && h.pr.split > h.q.split) ? h.pr.split : h.q.split;
 }
 
 int edrl_mmd_sweep_plan(int n_s, int n_t, int d, int flags, int row_count, int row_count2, int sms, int *plan) {
@@ -588,8 +666,11 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
   p.partial = partial; p.loss = loss; p.stats_out = stats;
   p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
-  const SweepPlan pl = make_plan(L, row_count, row_count2);
+  const HybridPlan hy = make_hybrid(L, row_count, row_count2);
+  const SweepPlan pl = hy.q;
   p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.items = pl.items;
+  p.panel0 = 0;
+  p.ticket_total = hy.on ? 4 * hy.q.pairs + 2 * hy.pr.pairs : 0;
   p.rowsum = reinterpret_cast<float *>(ws + L.off_rowsum);
   dim3 grid2((pl.quad ? 4 : 2) * pl.pairs, 1, 1);
   if (pl.quad)      // the two pairs of a cluster ADD their partial row sums
@@ -634,6 +715,22 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
     CUtensorMap tm_z128;
     if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
     if (pl.quad) {
+      if (hy.on) {
+        // the quad clusters first (they need whole groups of 4 SMs inside a GPC), then the pair part on the forked
+        // stream: its few clusters land on the SMs the quad grid left over
+        ForkJoin fj;
+        if (int rc = fj.fork(st)) return rc;
+        BwdParams pp = p;
+        pp.panels = hy.pr.panels; pp.full_items = hy.pr.full_items; pp.split = hy.pr.split; pp.items = hy.pr.items;
+        pp.panel0 = hy.q.panels;
+        const dim3 gridp(2 * hy.pr.pairs, 1, 1);
+        const int rc2 = fast ? launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st)
+                             : launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+        const int rc1 = fast ? launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side)
+                             : launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side);
+        const int rc3 = fj.join(st);
+        return rc1 ? rc1 : (rc2 ? rc2 : rc3);
+      }
       if (fast) return launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
       return launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
     }
@@ -652,7 +749,9 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n, "MK_MMD apply_grad: bad row range");
   const uint8_t *ws = reinterpret_cast<const uint8_t *>(workspace);
   const int rows = row_count + row_count2;
-  const SweepPlan pl = make_plan(L, row_count, row_count2);
+  const HybridPlan hy = make_hybrid(L, row_count, row_count2);
+  const ApplyPlan pa{hy.q.panels, hy.q.full_items, hy.q.split, hy.q.pass_feats};
+  const ApplyPlan pb{hy.pr.panels, hy.pr.full_items, hy.pr.split, hy.pr.pass_feats};
   const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
   const float *zlo = L.split3 ? reinterpret_cast<const float *>(ws + L.off_zlo) : nullptr;
   const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
@@ -661,11 +760,11 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
   if (v4)
     mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                      row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split, pl.pass_feats,
+                                                      row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
         reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   else
     mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pl.panels, pl.full_items, pl.split, pl.pass_feats,
+                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
         reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
   EDRL_LAUNCHED();
   return 0;

@@ -59,6 +59,10 @@ struct BwdParams {
   // mmd_sweep256_kernel work list (make_plan): virtual panel = (feature pass, row panel); the first `full_items` virtual
   // panels sweep all column groups, every later one is split into `split` column slabs with one partial output each
   int panels, full_items, split, items;
+  // a launch may own only the row panels [panel0, panel0 + panels) of the call's row ranges (the hybrid quad + pair launch
+  // for d > 768 gives the last panels to a pair kernel on the SMs the 4-CTA clusters cannot use); ticket_total = CTAs of
+  // all launches that share the accumulators (0: this launch alone)
+  int panel0, ticket_total;
   float *rowsum;                   // [feature pass][SW_MAX_SPLIT][n_pad]: rowsum(G')_i per column slab, for apply_grad
 };
 

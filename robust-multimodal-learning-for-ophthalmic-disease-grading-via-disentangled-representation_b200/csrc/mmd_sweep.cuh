@@ -83,7 +83,7 @@ __device__ __forceinline__ SweepItem sweep_item(const BwdParams &p, int item, in
   }
   it.ng = g_end - it.g_begin;
   it.ypass = vp / p.panels;
-  const int panel = vp - it.ypass * p.panels;
+  const int panel = p.panel0 + (vp - it.ypass * p.panels);   // index in the call's panel list (range 1, then range 2)
   const int np1 = (p.row_count + BM - 1) / BM;
   const bool second = panel >= np1;
   const int lpanel = second ? panel - np1 : panel;
@@ -574,7 +574,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       atomicAdd(p.acc + 1, dd);
       __threadfence();
       const unsigned t = atomicAdd(p.ticket, 1u);
-      if (t == gridDim.x - 1) {
+      if (t == (p.ticket_total > 0 ? (unsigned)p.ticket_total : gridDim.x) - 1) {
         __threadfence();
         const double Mv = atomicAdd(p.acc + 0, 0.0);
         const double Ds = atomicAdd(p.acc + 1, 0.0);
@@ -1093,7 +1093,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
       atomicAdd(p.acc + 1, dd);
       __threadfence();
       const unsigned t = atomicAdd(p.ticket, 1u);
-      if (t == gridDim.x - 1) {
+      if (t == (p.ticket_total > 0 ? (unsigned)p.ticket_total : gridDim.x) - 1) {
         __threadfence();
         const double Mv = atomicAdd(p.acc + 0, 0.0);
         const double Ds = atomicAdd(p.acc + 1, 0.0);
@@ -1116,14 +1116,17 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
 
 // dZ[i, f] = g sign(M) 4 (U[i, f] + c (n z_i[f] - sum_j z_j[f])) -- the closed-form bandwidth term on top of the
 // fused pass, on the same rounded centred operand the sweep used (sum_j z_j is its column sum, ~0 but not 0);
+struct ApplyPlan {                // the part of a SweepPlan edrl_mmd_apply_grad needs to find a row's partial outputs
+  int panels, full_items, split, pass_feats;
+};
 // one block row per output row (no per-element division), 128-bit accesses when d % 4 == 0
 template <bool VEC4>
 __global__ void __launch_bounds__(128)
 mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ zlo,
                       const double *__restrict__ colsum_hi,
                       const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
-                      int row_begin2, int row_count2, int d, int d_pad, int n, int n_pad, int panels, int full_items,
-                      int split, int pass_feats, const float *__restrict__ rowsum, float *__restrict__ dz) {
+                      int row_begin2, int row_count2, int d, int d_pad, int n, int n_pad, ApplyPlan pa, ApplyPlan pb,
+                      const float *__restrict__ rowsum, float *__restrict__ dz) {
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];
@@ -1136,7 +1139,12 @@ mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi
   const float *ur = U + (size_t)r * d;
   float *orow = dz + (size_t)r * d;
   // the sweep's work list (make_plan): virtual panel (feature pass, row panel) >= full_items was swept in `split` slabs
-  const int panel = (r < row_count) ? r / BM : (row_count + BM - 1) / BM + (r - row_count) / BM;
+  const int gpanel = (r < row_count) ? r / BM : (row_count + BM - 1) / BM + (r - row_count) / BM;
+  // which launch swept this row's panel: the first pa.panels panels plan A (the quad kernel in a hybrid launch), the rest B
+  const bool in_b = gpanel >= pa.panels;
+  const int panel = in_b ? gpanel - pa.panels : gpanel;
+  const int panels = in_b ? pb.panels : pa.panels, full_items = in_b ? pb.full_items : pa.full_items;
+  const int split = in_b ? pb.split : pa.split, pass_feats = in_b ? pb.pass_feats : pa.pass_feats;
   if (VEC4) {
     for (int f = (blockIdx.y * 128 + threadIdx.x) * 4; f < d; f += gridDim.y * 512) {
       const int yp = f / pass_feats;

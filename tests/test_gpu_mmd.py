@@ -605,3 +605,70 @@ def test_binary16_container_modes_are_numerically_the_tf32_result():
         l.backward()
         assert np.isclose(l.item(), ref, rtol=1e-3), prec
         assert np.abs(xt.grad.cpu().numpy() - dxr).max() <= 2e-3 * np.abs(dxr).max(), prec
+
+
+_HYBRID_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import edrl_b200
+ns, nt, d = int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+g = torch.Generator(device="cuda").manual_seed(99)
+x = torch.randn(ns, d, device="cuda", generator=g, requires_grad=True)
+y = (torch.randn(nt, d, device="cuda", generator=g) * 1.2 + 0.05).requires_grad_(True)
+loss = edrl_b200.MK_MMD(x, y, precision="tf32")
+loss.backward()
+out = dict(loss=loss.item(), gx=x.grad.cpu().numpy(), gy=y.grad.cpu().numpy())
+# the same step captured in a CUDA graph: the forked stream of the hybrid launch has to join the capture
+xs, ys = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(2):
+        xs.grad = None; ys.grad = None
+        edrl_b200.MK_MMD(xs, ys, precision="tf32").backward()
+torch.cuda.current_stream().wait_stream(side)
+cg = torch.cuda.CUDAGraph()
+xs.grad.zero_(); ys.grad.zero_()
+with torch.cuda.graph(cg):
+    l2 = edrl_b200.MK_MMD(xs, ys, precision="tf32")
+    l2.backward()
+xs.grad.zero_()
+cg.replay()
+torch.cuda.synchronize()
+out["graph_loss"] = l2.item()
+out["graph_gx"] = xs.grad.cpu().numpy()
+np.savez(sys.argv[2], **out)
+"""
+
+
+@pytest.mark.parametrize("ns,nt,d", [(1500, 1400, 1024), (700, 650, 1100)])
+def test_hybrid_quad_plus_pair_launch_matches_the_single_launch(tmp_path, ns, nt, d):
+    """d > 768: the last row panels go to a pair kernel on a forked stream next to the 4-CTA-cluster kernel
+    (csrc/mmd.cu make_hybrid).  Forced here on a small shape (EDRL_MMD_HYBRID=2 is read once per process, hence the child
+    processes) and compared with the single launch (=0) and the fp64 oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "2"):
+        path = str(tmp_path / f"h{mode}.npz")
+        env = dict(os.environ, EDRL_MMD_HYBRID=mode)
+        r = subprocess.run([sys.executable, "-c", _HYBRID_CHILD, root, path, str(ns), str(nt), str(d)], env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = np.load(path)
+    a, b = res["0"], res["2"]
+    gmax = float(np.abs(a["gx"]).max())
+    assert abs(float(a["loss"]) - float(b["loss"])) <= 2e-6 * max(1.0, abs(float(a["loss"])))
+    assert np.abs(a["gx"] - b["gx"]).max() <= 2e-5 * gmax          # same products, different summation order of the slabs
+    assert np.abs(a["gy"] - b["gy"]).max() <= 2e-5 * float(np.abs(a["gy"]).max())
+    assert abs(float(b["graph_loss"]) - float(b["loss"])) <= 1e-6
+    assert np.abs(b["graph_gx"] - b["gx"]).max() <= 2e-5 * gmax
+    # and against the fp64 oracle
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = torch.randn(ns, d, device="cuda", generator=g)
+    y = torch.randn(nt, d, device="cuda", generator=g) * 1.2 + 0.05
+    want, _, gx, gy = O.mk_mmd_grad(x.cpu().numpy(), y.cpu().numpy())
+    tol = dict((m[0], m) for m in MODES)["tf32"]
+    assert np.isclose(float(b["loss"]), want, rtol=tol[2], atol=1e-6)
+    assert np.abs(b["gx"] - gx).max() <= tol[3] * max(np.abs(gx).max(), np.abs(gy).max())
