@@ -20,11 +20,12 @@ constexpr int SW_MAX_SPLIT = 8;                // column slabs of a split virtua
 // MODE 0: TF32 everywhere.  1 (EDRL_MMD_TF32H): binary16 P phase.  2 (EDRL_MMD_F16S): the S phase too reads scaled
 // binary16 operands (Z16, kind::f16): a ring stage then holds 64 feature columns instead of 32.
 // The binary16 modes keep TWO G buffers (32 KiB each), so the epilogue of group g+1 overlaps the P phase of group g.
-// MODE 3 (EDRL_MMD_3XTF32): hi / lo split operands, three TF32 MMAs per product, fp32-level accuracy -- as ONE long
-// contraction each way.  S = Z_hi Z_hi^T + Z_lo Z_hi^T + Z_hi Z_lo^T is the TF32 Gram of [hi | lo | hi] against
-// [hi | hi | lo]: the K loop simply runs over three parts, the producer picking the hi or lo rows of the operand maps.
-// P the same over the column group: K atoms (Z_hi^T, G_hi), (Z_hi^T, G_lo), (Z_lo^T, G_hi); G is written as its TF32 hi
-// and lo parts (2 x 64 KiB), which leaves 5 ring stages instead of 9.
+// MODE 3 (EDRL_MMD_3XTF32): hi / lo split operands, three TF32 MMAs per product, fp32-level accuracy, in the same
+// accumulators.  S = Z_hi Z_hi^T + Z_lo Z_hi^T + Z_hi Z_lo^T: per 32-column K chunk the producer fetches [Z_I hi | Z_I lo],
+// Z_J hi and Z_J lo (the lo rows of the operand maps sit below the hi rows) and the issuer forms the three products, so
+// every hi chunk is fetched ONCE for its two products (2/3 of the bytes of three independent passes -- the sweep is bound
+// by L2 -> SM ingest).  P the same over the column group: the Z_hi^T stage meets G_hi and G_lo, the Z_lo^T stage G_hi; G
+// is written as its TF32 hi and lo parts (2 x 64 KiB), which leaves 5 ring stages instead of 9.
 template <int MODE>
 struct SweepCfg {
   static constexpr bool H16 = MODE == 1 || MODE == 2;
@@ -35,7 +36,7 @@ struct SweepCfg {
   static constexpr int G_BUFS = H16 ? 2 : 1;
   static constexpr int STAGES = X3 ? 5 : 9;
   static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
-  static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : (X3 ? 3 * (Q_GROUP / BK) : Q_GROUP / BK);   // K atoms per column group
+  static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : (X3 ? 2 * (Q_GROUP / BK) : Q_GROUP / BK);   // ring stages per column group and dZ^T tile
   static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
 };
 
@@ -127,7 +128,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
   const int kch1 = S16 ? p.d_pad / 64 : p.kchunks;        // 128-byte K chunks of an S operand row; even
-  const int kchunks = X3 ? 3 * kch1 : kch1;                // 3xTF32: the parts [hi | lo | hi] x [hi | hi | lo] in one K loop
+  const int kchunks = kch1;                               // (3xTF32 walks kch1 single chunks, three ring stages each)
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (threadIdx.x == 0) {
@@ -184,24 +185,41 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       const int irow = it.row_base + (int)rank * 64;
       auto load_S = [&](int g) {
         const int jrow = (it.g_begin + g) * Q_GROUP + (int)rank * 128;
+        if (X3) {
+          // 3xTF32, per 32-column K chunk three stages: [Z_I hi | Z_I lo] (64 rows each), Z_J hi, Z_J lo (128 rows each;
+          // the lo rows sit n_pad rows below the hi rows in both maps).  The issuer forms hi x hi, lo x hi and hi x lo
+          // from them: each hi chunk is fetched once for its two products (48 KiB per chunk instead of 72).
+          for (int kk = 0; kk < kch1; ++kk) {
+            {
+              uint8_t *st = acquire();
+              const uint32_t bar = full0 + 8u * (uint32_t)s;
+              tma_load_2d_pair_elect(st, &tm_z64, bar, kk * Cfg::S_COLS, irow);
+              tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, kk * Cfg::S_COLS, irow + p.n_pad);
+              next();
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint8_t *st = acquire();
+              const uint32_t bar = full0 + 8u * (uint32_t)s;
+              tma_load_2d_pair_elect(st, &tm_z128, bar, kk * Cfg::S_COLS, jrow + h * p.n_pad);
+              next();
+            }
+          }
+          return;
+        }
         for (int kc = 0; kc < kchunks; kc += 2) {
-          // 3xTF32: part 0 = hi x hi, 1 = lo x hi, 2 = hi x lo; the lo rows sit n_pad rows below the hi rows in both maps
-          const int part = X3 ? kc / kch1 : 0;
-          const int kk = kc - part * kch1;
-          const int ia = irow + ((X3 && part == 1) ? p.n_pad : 0);
-          const int jb = jrow + ((X3 && part == 2) ? p.n_pad : 0);
           {                                                   // two chunks of this CTA's 64 panel rows
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_z64, bar, kk * Cfg::S_COLS, ia);
-            tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kk + 1) * Cfg::S_COLS, ia);
+            tma_load_2d_pair_elect(st, &tm_z64, bar, kc * Cfg::S_COLS, irow);
+            tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * Cfg::S_COLS, irow);
             next();
           }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {                       // one chunk of this CTA's 128 rows of the column group each
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_z128, bar, (kk + h) * Cfg::S_COLS, jb);
+            tma_load_2d_pair_elect(st, &tm_z128, bar, (kc + h) * Cfg::S_COLS, jrow);
             next();
           }
         }
@@ -211,9 +229,9 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           for (int a8 = 0; a8 < Cfg::P_ATOMS; ++a8) {
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
-            // 3xTF32: atoms 0-7 and 8-15 read Z_hi^T (against G_hi, G_lo), 16-23 Z_lo^T (d_pad rows below, against G_hi)
-            const int ac = X3 ? (a8 & 7) : a8;
-            const int fr = it.f0 + t * 256 + (int)rank * 128 + ((X3 && a8 >= 16) ? p.d_pad : 0);
+            // 3xTF32: stage 2a holds K atom a of Z_hi^T (for G_hi and G_lo), stage 2a + 1 of Z_lo^T (d_pad rows below, for G_hi)
+            const int ac = X3 ? (a8 >> 1) : a8;
+            const int fr = it.f0 + t * 256 + (int)rank * 128 + ((X3 && (a8 & 1)) ? p.d_pad : 0);
             tma_load_2d_pair_elect(st, &tm_zt, bar, (it.g_begin + g) * Q_GROUP + ac * Cfg::P_ATOM_COLS, fr);
             next();
           }
@@ -249,7 +267,38 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
           mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_s + b * 128;
-          for (int kc = 0; kc < kchunks; kc += 2) {
+          if (X3) {
+            for (int kk = 0; kk < kch1; ++kk) {
+              mbar_wait(&ctl->full[s], ph);                  // [Z_I hi | Z_I lo] of this chunk
+              tc_fence_after();
+              const int sa = s;
+              const uint64_t a_hi = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+              const uint64_t a_lo = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE + P2_CHUNK);
+              next();
+              mbar_wait(&ctl->full[s], ph);                  // Z_J hi: hi x hi, lo x hi
+              tc_fence_after();
+              const uint64_t b_hi = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_tf32_ss_pair_elect(d_tmem, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc_s,
+                                       (kk > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_tf32_ss_pair_elect(d_tmem, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc_s, 1u);
+              mma_commit_pair_elect(&ctl->empty[s]);
+              next();
+              mbar_wait(&ctl->full[s], ph);                  // Z_J lo: hi x lo
+              tc_fence_after();
+              const uint64_t b_lo = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_tf32_ss_pair_elect(d_tmem, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc_s, 1u);
+              mma_commit_pair_elect(&ctl->empty[sa]);
+              mma_commit_pair_elect(&ctl->empty[s]);
+              next();
+            }
+          }
+          for (int kc = 0; kc < (X3 ? 0 : kchunks); kc += 2) {
             mbar_wait(&ctl->full[s], ph);                    // the Z_I stage (two chunks)
             tc_fence_after();
             const int sa = s;
@@ -286,8 +335,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
               mbar_wait(&ctl->full[s], ph);
               tc_fence_after();
               const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-              // (3xTF32: G atoms 0-7 hold G_hi, 8-15 G_lo; K atoms 16-23 pair Z_lo^T with G_hi again)
-              const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + ((X3 && a8 >= 16) ? a8 - 16 : a8) * P2_CHUNK);
+              // (3xTF32: G atoms 0-7 hold G_hi, 8-15 G_lo; the Z_hi^T stage 2a meets both, the Z_lo^T stage 2a + 1 G_hi)
+              const uint64_t b_d = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + (X3 ? (a8 >> 1) : a8) * P2_CHUNK);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {                 // 32-byte K steps: 8 TF32 or 16 binary16 values
                 const uint64_t adv = (uint64_t)(k * 2);
@@ -297,6 +346,12 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
                 else
                   mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
                                          (g > 0 || a8 > 0 || k > 0) ? 1u : 0u);
+              }
+              if (X3 && !(a8 & 1)) {
+                const uint64_t b_lo = make_kmajor_sw128_desc(g_addr + gb * Cfg::G_BYTES + (8 + (a8 >> 1)) * P2_CHUNK);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc_p, 1u);
               }
               mma_commit_pair_elect(&ctl->empty[s]);
               next();
