@@ -588,7 +588,7 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
   p.acc = nullptr; p.ticket = nullptr; p.partial = nullptr; p.loss = nullptr; p.stats_out = nullptr;
   p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0; p.fscale = nullptr;
-  p.panel0 = 0; p.ticket_total = 0;
+  p.panel0 = 0; p.ticket_total = 0; p.s_ahead = 0;
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
   if (!L.split3 && !legacy) {
@@ -670,6 +670,10 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   const SweepPlan pl = hy.q;
   p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.items = pl.items;
   p.panel0 = 0;
+  {
+    static const int order = getenv("EDRL_MMD_QUAD_ORDER") ? atoi(getenv("EDRL_MMD_QUAD_ORDER")) : 1;   // A/B runs
+    p.s_ahead = order;
+  }
   p.ticket_total = hy.on ? 4 * hy.q.pairs + 2 * hy.pr.pairs : 0;
   p.rowsum = reinterpret_cast<float *>(ws + L.off_rowsum);
   dim3 grid2((pl.quad ? 4 : 2) * pl.pairs, 1, 1);

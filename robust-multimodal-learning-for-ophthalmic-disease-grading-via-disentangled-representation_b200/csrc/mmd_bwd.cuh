@@ -63,6 +63,7 @@ struct BwdParams {
   // for d > 768 gives the last panels to a pair kernel on the SMs the 4-CTA clusters cannot use); ticket_total = CTAs of
   // all launches that share the accumulators (0: this launch alone)
   int panel0, ticket_total;
+  int s_ahead;                 // quad sweep: issue order of the S phases (mmd_sweep_quad_kernel)
   float *rowsum;                   // [feature pass][SW_MAX_SPLIT][n_pad]: rowsum(G')_i per column slab, for apply_grad
 };
 

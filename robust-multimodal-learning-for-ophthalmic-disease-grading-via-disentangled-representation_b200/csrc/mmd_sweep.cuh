@@ -684,6 +684,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
   const int npairs = gridDim.x >> 2;
   auto owns = [&](int g) { return (g & 1) == pairidx; };  // which pair computes S / G of column group g of an item
   const int kchunks = S16 ? p.d_pad / 64 : p.kchunks;     // 128-byte K chunks of an S operand row; even
+  const int khalf = (kchunks / 4) * 2;                    // an S phase is issued as the K halves [0, khalf), [khalf, kchunks)
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   if (threadIdx.x == 0) {
@@ -742,9 +743,9 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
     for (int item = pair; item < p.items; item += npairs) {
       const SweepItem it = sweep_item(p, item, pairidx);
       const int irow = it.row_base + (int)rank * 64;
-      auto load_S = [&](int g) {
+      auto load_S = [&](int g, int k_begin, int k_end) {
         const int jrow = (it.g_begin + g) * Q_GROUP + (int)rank * 128;
-        for (int kc = 0; kc < kchunks; kc += 2) {
+        for (int kc = k_begin; kc < k_end; kc += 2) {
           {                                                   // two chunks of this CTA's 64 panel rows
             uint8_t *st = acquire();
             const uint32_t bar = full0 + 8u * (uint32_t)s;
@@ -771,10 +772,22 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
             next();
           }
       };
-      if (owns(0)) load_S(0);
-      for (int g = 0; g < it.ng; ++g) {
-        if (g + 1 < it.ng && owns(g + 1)) load_S(g + 1);
-        load_P(g);
+      // the issue order of the MMA warp (see there): S of this pair's first two groups, then per group P(g) followed by
+      // one half of an S phase two own groups ahead
+      if (p.s_ahead) {
+        if (pairidx < it.ng) load_S(pairidx, 0, kchunks);
+        if (pairidx + 2 < it.ng) load_S(pairidx + 2, 0, kchunks);
+        for (int g = 0; g < it.ng; ++g) {
+          load_P(g);
+          if (g + 4 < it.ng && owns(g + 4)) load_S(g + 4, 0, khalf);
+          if (g >= 1 && g + 3 < it.ng && owns(g + 3)) load_S(g + 3, khalf, kchunks);
+        }
+      } else {
+        if (owns(0)) load_S(0, 0, kchunks);
+        for (int g = 0; g < it.ng; ++g) {
+          if (g + 1 < it.ng && owns(g + 1)) load_S(g + 1, 0, kchunks);
+          load_P(g);
+        }
       }
     }
   } else if (warp == 1) {
@@ -797,13 +810,16 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
       int itn = 0;                                         // running item counter
       for (int item = pair; item < p.items; item += npairs, ++itn) {
         const SweepItem it = sweep_item(p, item, pairidx);
-        auto issue_S = [&](int c) {                        // c: running index of the group
+        // K chunks [k_begin, k_end) of the S phase number c of this pair (c: running index of its own groups)
+        auto issue_S = [&](int c, int k_begin, int k_end) {
           const int b = c & 1;
           const uint32_t u = (uint32_t)(c >> 1);
-          mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
-          tc_fence_after();
+          if (k_begin == 0) {
+            mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
+            tc_fence_after();
+          }
           const uint32_t d_tmem = tmem_s + b * 128;
-          for (int kc = 0; kc < kchunks; kc += 2) {
+          for (int kc = k_begin; kc < k_end; kc += 2) {
             mbar_wait(&ctl->full[s], ph);                    // the Z_I stage (two chunks)
             tc_fence_after();
             const int sa = s;
@@ -828,7 +844,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
               next();
             }
           }
-          mma_commit_mask_elect(&ctl->s_full[b], pmask);
+          if (k_end == kchunks) mma_commit_mask_elect(&ctl->s_full[b], pmask);
         };
         auto issue_P = [&](int g, int c) {                 // g: group inside the item, c: running index
           const int gb = c % GB;
@@ -856,14 +872,28 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
             }
           mma_commit_mask_elect(&ctl->g_empty[gb], pmask);
         };
-        if (owns(0)) issue_S(sc++);
+        // Order on the (in-order) tensor pipe: S of this pair's first two groups, then per group P(g) followed by HALF
+        // of the S phase of an own group two own groups ahead.  Every refill of the single G buffer -- the epilogue's
+        // write of G(g + 1) or the copy of the other pair's tile, both of which have to wait for P(g) to finish
+        // reading -- then happens under half an S phase instead of stalling the pipe, and the epilogue math of a group
+        // has two P phases and an S phase of slack.
+        if (p.s_ahead) {
+          if (pairidx < it.ng) issue_S(sc++, 0, kchunks);
+          if (pairidx + 2 < it.ng) issue_S(sc++, 0, kchunks);
+        } else if (owns(0)) {
+          issue_S(sc++, 0, kchunks);
+        }
         for (int g = 0; g < it.ng; ++g) {
-          if (g + 1 < it.ng && owns(g + 1)) issue_S(sc++);
+          if (!p.s_ahead && g + 1 < it.ng && owns(g + 1)) issue_S(sc++, 0, kchunks);
           if (g == 0 && itn > 0) {                         // the previous item's dZ^T has been read out of TMEM
             mbar_wait_cluster(&ctl->dz_empty, (uint32_t)((itn - 1) & 1));
             tc_fence_after();
           }
           issue_P(g, gc + g);
+          if (p.s_ahead) {
+            if (g + 4 < it.ng && owns(g + 4)) issue_S(sc, 0, khalf);
+            if (g >= 1 && g + 3 < it.ng && owns(g + 3)) issue_S(sc++, khalf, kchunks);
+          }
         }
         gc += it.ng;
         mma_commit_mask_elect(&ctl->dz_full, pmask);
