@@ -19,6 +19,7 @@
 //   dZ_i = g sign(M) 4 (rowsum(G)_i z_i - (G Z)_i).
 // Centring Z (distances are translation invariant) keeps TF32 rounding relative to the spread of the data
 // and makes sum(L) = 2 n sum_i |z_i|^2 exactly the reference's bandwidth statistic (code/MMD.py:31).
+#include <mutex>
 #include <math.h>
 #include <stdlib.h>
 
@@ -452,12 +453,17 @@ static SweepPlan make_plan(const Layout &L, int row_count, int row_count2, int s
 struct ForkJoin {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // the side stream and its two events are shared by every call on the device: host threads take turns from fork() to
+  // join() (enqueue calls only), or one thread's wait could pick up the other's record
+  std::unique_lock<std::mutex> turn;
   int fork(cudaStream_t main) {
+    static std::mutex s_mutex[16];
     static cudaStream_t s_side[16] = {};
     static cudaEvent_t s_ev[16][2] = {};
     int dev = 0;
     EDRL_CUDA_OK(cudaGetDevice(&dev));
     EDRL_CHECK_ARG(dev >= 0 && dev < 16, "MK_MMD: device index %d not supported by the hybrid launch", dev);
+    turn = std::unique_lock<std::mutex>(s_mutex[dev]);
     if (s_side[dev] == nullptr) {
       EDRL_CUDA_OK(cudaStreamCreateWithFlags(&s_side[dev], cudaStreamNonBlocking));
       EDRL_CUDA_OK(cudaEventCreateWithFlags(&s_ev[dev][0], cudaEventDisableTiming));
