@@ -824,7 +824,7 @@ def run_ours(args, rank, local_rank, world):
         ach_f = flops_f / (f_ms * 1e-3) / 1e12
         fwd_info = {"kernel": "prep + mmd_fwd_pair_kernel (loss only, e.g. under no_grad)", "ms": f_ms,
                     "achieved": ach_f, "frac": ach_f / peak, "algorithmic_flops": flops_f}
-        bwd_info = {"kernel": "mmd_bwd_pair_kernel (separate tile-recomputing backward)", "ms": b_ms,
+        bwd_info = {"kernel": "edrl_mmd_backward: the sweep kernel + apply_grad in place (3xtf32: mmd_bwd_kernel)", "ms": b_ms,
                     "achieved": ach_b, "frac": ach_b / peak, "algorithmic_flops": flops_b}
         if prec in ("tf32", "tf32h", "f16s", "3xtf32") and not (prec == "3xtf32" and d > 768):
             # the training step's dominant launch: forward sums + gradient in one sweep over the Gram tiles

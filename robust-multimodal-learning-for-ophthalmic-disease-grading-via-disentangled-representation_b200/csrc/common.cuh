@@ -66,7 +66,10 @@ struct DeviceGuard {
       prev = dev = -1;
       return;
     }
-    if (dev != prev && cudaSetDevice(dev) != cudaSuccess) {
+    // (also when dev == prev: cudaSetDevice binds the device's primary context to THIS thread.  A host framework's worker
+    //  thread -- torch's autograd thread -- may have a device selected and no context current yet; driver entry points
+    //  such as cuTensorMapEncodeTiled then fail with CUDA_ERROR_INVALID_CONTEXT when they are the thread's first call)
+    if (cudaSetDevice(dev) != cudaSuccess) {
       (void)cudaGetLastError();
       prev = dev = -1;
     }

@@ -5,7 +5,8 @@
 //   mmd_fwd.cuh    K2   loss-only forward: persistent, warp-specialised TMA -> smem ring -> tcgen05.mma (kind::tf32) ->
 //                       TMEM -> fused distance / exp-sum / block-reduce epilogue over upper-triangular tiles
 //                       (mmd_fwd_pair_kernel: 256 x 256 tiles, cta_group::2; mmd_fwd_kernel: 128 x 128, 3xTF32, K matrix)
-//   mmd_bwd.cuh    K3   separate tile-recomputing backward (mmd_bwd_pair_kernel, mmd_bwd_kernel for 3xTF32)
+//   mmd_bwd.cuh    K3   the first tile-recomputing backward (mmd_bwd_kernel: 3xTF32 beyond the fused sweep, A/B runs); the
+//                       TF32-family edrl_mmd_backward runs the sweep + apply_grad in place
 //   mmd_sweep.cuh  K3q  the training path: fused forward sums + gradient in one persistent sweep over the Gram tiles
 //                       (mmd_sweep256_kernel: CTA pairs; mmd_sweep_quad_kernel: 4-CTA clusters for d > 768) and
 //                       mmd_apply_grad_kernel
@@ -320,18 +321,6 @@ static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtens
 
 #include "mmd_sweep.cuh"
 
-template <bool FAST, int RES>
-static int launch_bwd_pair_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_zt, const BwdParams &p, dim3 grid,
-                             cudaStream_t st) {
-  using Cfg = Bwd2Cfg<RES>;
-  auto kern = mmd_bwd_pair_kernel<FAST, RES>;
-  // per launch (cheap): the attribute is per device, a process may drive several
-  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(tm_z64, tm_zt, p);
-  EDRL_LAUNCHED();
-  return 0;
-}
-
 template <bool FAST, int MODE = 0>
 static int launch_sweep_quad_t(const CUtensorMap &tm_z64, const CUtensorMap &tm_z128, const CUtensorMap &tm_zt,
                                const BwdParams &p, dim3 grid, cudaStream_t st) {
@@ -403,7 +392,7 @@ static bool quad_wanted(const Layout &L) {
 
 // force_kind: -1 = by width, 0 = pair kernel, 1 = quad kernel; clusters_override: persistent clusters available (hybrid)
 static SweepPlan make_plan_panels(const Layout &L, int panels, int sms_override = 0, int force_kind = -1,
-                                  int clusters_override = 0) {
+                                  int clusters_override = 0, int max_split = SW_MAX_SPLIT) {
   SweepPlan pl;
   pl.panels = panels;
   pl.quad = (force_kind < 0 ? quad_wanted(L) : force_kind != 0) ? 1 : 0;
@@ -426,7 +415,7 @@ static SweepPlan make_plan_panels(const Layout &L, int panels, int sms_override 
   const int R = pl.vpanels - pl.full_items;
   pl.split = 1;
   static const char *env = getenv("EDRL_MMD_SLABS");      // =1: never split (A/B runs)
-  const int kmax = env ? atoi(env) : 8;
+  const int kmax = (env && atoi(env) < max_split) ? atoi(env) : max_split;
   if (R > 0) {
     double best = 1.0;
     for (int k = 2; k <= 8 && k <= kmax && k <= nG; k *= 2) {
@@ -518,6 +507,136 @@ static HybridPlan make_hybrid(const Layout &L, int row_count, int row_count2) {
 }
 
 
+static HybridPlan single_plan(const Layout &L, int row_count, int row_count2) {
+  HybridPlan h;
+  h.on = false;
+  h.q = make_plan_panels(L, (row_count + BM - 1) / BM + (row_count2 + BM - 1) / BM, 0, -1, 0, 1);
+  h.pr = h.q;
+  return h;
+}
+
+// The sweep of a prepared workspace over the row ranges [row_begin, +row_count) and [row_begin2, +row_count2): forward
+// block sums (into `partial`, or finalised into loss / stats) and U.  single: one launch, no column slabs (the plan
+// edrl_mmd_backward's in-place use needs: one U slab).
+static int launch_sweep(const Layout &L, uint8_t *ws, int n_s, int n_t, int d, float kernel_mul, int kernel_num,
+                        int row_begin, int row_count, int row_begin2, int row_count2, int finalize, float *loss,
+                        float *stats, double *partial, float *U, cudaStream_t st, bool single) {
+  CUtensorMap tm_z64, tm_zt;
+  if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
+  if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
+  BwdParams p;
+  p.n = L.n; p.n_s = n_s; p.n_pad = L.n_pad; p.d = d; p.d_pad = L.d_pad;
+  p.nb = L.n_pad / BN; p.kchunks = L.d_pad / BK; p.num = kernel_num; p.mul = kernel_mul;
+  p.row_begin = row_begin; p.row_count = row_count;
+  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
+  p.a = reinterpret_cast<const float *>(ws + L.off_a);
+  p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  p.zlo = nullptr;
+  p.stats = nullptr; p.grad_out = nullptr; p.dz = U;
+  p.acc = reinterpret_cast<double *>(ws + L.off_acc);
+  p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
+  p.partial = partial; p.loss = loss; p.stats_out = stats;
+  p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
+  const HybridPlan hy = single ? single_plan(L, row_count, row_count2) : make_hybrid(L, row_count, row_count2);
+  const SweepPlan pl = hy.q;
+  p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.items = pl.items;
+  p.panel0 = 0;
+  {
+    static const int order = getenv("EDRL_MMD_QUAD_ORDER") ? atoi(getenv("EDRL_MMD_QUAD_ORDER")) : 1;   // A/B runs
+    p.s_ahead = order;
+  }
+  p.ticket_total = hy.on ? 4 * hy.q.pairs + 2 * hy.pr.pairs : 0;
+  p.rowsum = reinterpret_cast<float *>(ws + L.off_rowsum);
+  dim3 grid2((pl.quad ? 4 : 2) * pl.pairs, 1, 1);
+  if (pl.quad)      // the two pairs of a cluster ADD their partial row sums
+    EDRL_CUDA_OK(cudaMemsetAsync(ws + L.off_rowsum, 0,
+                                 (size_t)((L.d_pad + 511) / 512) * SW_MAX_SPLIT * L.n_pad * sizeof(float), st));
+  const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
+  p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
+  if (L.split3) {
+    // 3xTF32: hi and lo parts behind one another -- rows [0, n_pad) of the S maps are Z_hi, [n_pad, 2 n_pad) Z_lo; rows
+    // [0, d_pad) of the P map are Z_hi^T, [d_pad, 2 d_pad) Z_lo^T
+    CUtensorMap tm3_z64, tm3_z128, tm3_zt;
+    if (int rc = make_tmap_2d_f32(&tm3_z64, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
+    if (int rc = make_tmap_2d_f32(&tm3_z128, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (int rc = make_tmap_2d_f32(&tm3_zt, ws + L.off_zthi, 2ull * L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
+    if (fast) return launch_sweep256_t<true, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
+    return launch_sweep256_t<false, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
+  }
+  if (L.h16) {
+    // binary16 (scaled) operands for G.Z; the Gram on TF32 (TF32H) or on the binary16 copy Z16 (F16S)
+    CUtensorMap tm_z128, tm_zt16;
+    if (int rc = make_tmap_2d_f16(&tm_zt16, ws + L.off_zt16, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 2, 128, 64)) return rc;
+    if (L.s16) {
+      CUtensorMap tm_z64h;
+      if (int rc = make_tmap_2d_f16(&tm_z64h, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 64, 64)) return rc;
+      if (int rc = make_tmap_2d_f16(&tm_z128, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 128, 64)) return rc;
+      if (pl.quad) {
+        if (fast) return launch_sweep_quad_t<true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+        return launch_sweep_quad_t<false, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+      }
+      if (fast) return launch_sweep256_t<true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+      return launch_sweep256_t<false, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
+    }
+    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (pl.quad) {
+      if (fast) return launch_sweep_quad_t<true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+      return launch_sweep_quad_t<false, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    }
+    if (fast) return launch_sweep256_t<true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+    return launch_sweep256_t<false, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
+  }
+  {
+    CUtensorMap tm_z128;
+    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
+    if (pl.quad) {
+      if (hy.on) {
+        // the quad clusters first (they need whole groups of 4 SMs inside a GPC), then the pair part on the forked
+        // stream: its few clusters land on the SMs the quad grid left over
+        ForkJoin fj;
+        if (int rc = fj.fork(st)) return rc;
+        BwdParams pp = p;
+        pp.panels = hy.pr.panels; pp.full_items = hy.pr.full_items; pp.split = hy.pr.split; pp.items = hy.pr.items;
+        pp.panel0 = hy.q.panels;
+        const dim3 gridp(2 * hy.pr.pairs, 1, 1);
+        const int rc2 = fast ? launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st)
+                             : launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+        const int rc1 = fast ? launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side)
+                             : launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side);
+        const int rc3 = fj.join(st);
+        return rc1 ? rc1 : (rc2 ? rc2 : rc3);
+      }
+      if (fast) return launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+      return launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+    }
+    if (fast) return launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+    return launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
+  }
+}
+
+static int launch_apply(const Layout &L, const uint8_t *ws, int d, const float *stats, const float *grad_out, const float *U,
+                        int row_begin, int row_count, int row_begin2, int row_count2, float *dZ, const HybridPlan &hy,
+                        cudaStream_t st) {
+  const int rows = row_count + row_count2;
+  const ApplyPlan pa{hy.q.panels, hy.q.full_items, hy.q.split, hy.q.pass_feats};
+  const ApplyPlan pb{hy.pr.panels, hy.pr.full_items, hy.pr.split, hy.pr.pass_feats};
+  const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
+  const float *zlo = L.split3 ? reinterpret_cast<const float *>(ws + L.off_zlo) : nullptr;
+  const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
+  const bool v4 = (d % 4 == 0) && ((((uintptr_t)U | (uintptr_t)dZ) & 15) == 0);
+  dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
+  if (v4)
+    mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
+                                                      row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
+        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
+  else
+    mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
+                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
+        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
+  EDRL_LAUNCHED();
+  return 0;
+}
+
 }  // namespace mmd
 }  // namespace edrl
 
@@ -598,20 +717,12 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
   const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
   static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
   if (!L.split3 && !legacy) {
-    // TF32: CTA-pair kernel (one Gram recompute per tile, Z_I resident for d <= 512)
-    CUtensorMap tm_z64, tm_zt;
-    if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
-    if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
-    dim3 grid2(2 * ((row_count + BM - 1) / BM), (L.d_pad + P2_FEATS - 1) / P2_FEATS);
-    // resident Z_I chunks: 8 of 16 for d <= 512 (measured: 16 -> 1.22 ms, 12 -> 1.10 ms, 8 -> 1.05 ms, 0 -> 1.12 ms
-    // at N=8192, d=512: more residency leaves too few ring stages), none beyond
-    const int res = (L.d_pad <= 512) ? 8 : 0;
-    if (res == 8) {
-      if (fast) return launch_bwd_pair_t<true, 8>(tm_z64, tm_zt, p, grid2, st);
-      return launch_bwd_pair_t<false, 8>(tm_z64, tm_zt, p, grid2, st);
-    }
-    if (fast) return launch_bwd_pair_t<true, 0>(tm_z64, tm_zt, p, grid2, st);
-    return launch_bwd_pair_t<false, 0>(tm_z64, tm_zt, p, grid2, st);
+    // TF32 and its binary16-container modes: the fused sweep (its forward sums are a by-product nobody reads here) writes
+    // U into dZ, apply_grad finishes it in place -- one U slab, hence the single-launch plan
+    if (int rc = launch_sweep(L, ws, n_s, n_t, d, kernel_mul, kernel_num, row_begin, row_count, 0, 0, 0, nullptr, nullptr,
+                              nullptr, dZ, st, true))
+      return rc;
+    return launch_apply(L, ws, d, stats, grad_out, dZ, row_begin, row_count, 0, 0, dZ, single_plan(L, row_count, 0), st);
   }
   dim3 grid((row_count + BM - 1) / BM, (d + DC - 1) / DC);
   if (L.split3) {
@@ -656,97 +767,8 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
   if (int rc = run_prep(X, Y, n_s, n_t, d, L, ws, st, !L.h16)) return rc;
-  CUtensorMap tm_z64, tm_zt;
-  if (int rc = make_tmap_2d_f32(&tm_z64, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
-  if (int rc = make_tmap_2d_f32(&tm_zt, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
-  BwdParams p;
-  p.n = L.n; p.n_s = n_s; p.n_pad = L.n_pad; p.d = d; p.d_pad = L.d_pad;
-  p.nb = L.n_pad / BN; p.kchunks = L.d_pad / BK; p.num = kernel_num; p.mul = kernel_mul;
-  p.row_begin = row_begin; p.row_count = row_count;
-  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
-  p.a = reinterpret_cast<const float *>(ws + L.off_a);
-  p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
-  p.zlo = nullptr;
-  p.stats = nullptr; p.grad_out = nullptr; p.dz = U;
-  p.acc = reinterpret_cast<double *>(ws + L.off_acc);
-  p.ticket = reinterpret_cast<unsigned *>(ws + L.off_acc + 128);
-  p.partial = partial; p.loss = loss; p.stats_out = stats;
-  p.n_t = n_t; p.finalize = finalize; p.row_begin2 = row_begin2; p.row_count2 = row_count2;
-  const HybridPlan hy = make_hybrid(L, row_count, row_count2);
-  const SweepPlan pl = hy.q;
-  p.panels = pl.panels; p.full_items = pl.full_items; p.split = pl.split; p.items = pl.items;
-  p.panel0 = 0;
-  {
-    static const int order = getenv("EDRL_MMD_QUAD_ORDER") ? atoi(getenv("EDRL_MMD_QUAD_ORDER")) : 1;   // A/B runs
-    p.s_ahead = order;
-  }
-  p.ticket_total = hy.on ? 4 * hy.q.pairs + 2 * hy.pr.pairs : 0;
-  p.rowsum = reinterpret_cast<float *>(ws + L.off_rowsum);
-  dim3 grid2((pl.quad ? 4 : 2) * pl.pairs, 1, 1);
-  if (pl.quad)      // the two pairs of a cluster ADD their partial row sums
-    EDRL_CUDA_OK(cudaMemsetAsync(ws + L.off_rowsum, 0,
-                                 (size_t)((L.d_pad + 511) / 512) * SW_MAX_SPLIT * L.n_pad * sizeof(float), st));
-  const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
-  p.fscale = reinterpret_cast<const int *>(ws + L.off_fscale);
-  if (L.split3) {
-    // 3xTF32: hi and lo parts behind one another -- rows [0, n_pad) of the S maps are Z_hi, [n_pad, 2 n_pad) Z_lo; rows
-    // [0, d_pad) of the P map are Z_hi^T, [d_pad, 2 d_pad) Z_lo^T
-    CUtensorMap tm3_z64, tm3_z128, tm3_zt;
-    if (int rc = make_tmap_2d_f32(&tm3_z64, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 64, BK)) return rc;
-    if (int rc = make_tmap_2d_f32(&tm3_z128, ws + L.off_zhi, 2ull * L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
-    if (int rc = make_tmap_2d_f32(&tm3_zt, ws + L.off_zthi, 2ull * L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, 128, BK)) return rc;
-    if (fast) return launch_sweep256_t<true, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
-    return launch_sweep256_t<false, 3>(tm3_z64, tm3_z128, tm3_zt, p, grid2, st);
-  }
-  if (L.h16) {
-    // binary16 (scaled) operands for G.Z; the Gram on TF32 (TF32H) or on the binary16 copy Z16 (F16S)
-    CUtensorMap tm_z128, tm_zt16;
-    if (int rc = make_tmap_2d_f16(&tm_zt16, ws + L.off_zt16, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 2, 128, 64)) return rc;
-    if (L.s16) {
-      CUtensorMap tm_z64h;
-      if (int rc = make_tmap_2d_f16(&tm_z64h, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 64, 64)) return rc;
-      if (int rc = make_tmap_2d_f16(&tm_z128, ws + L.off_z16, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 2, 128, 64)) return rc;
-      if (pl.quad) {
-        if (fast) return launch_sweep_quad_t<true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
-        return launch_sweep_quad_t<false, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
-      }
-      if (fast) return launch_sweep256_t<true, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
-      return launch_sweep256_t<false, 2>(tm_z64h, tm_z128, tm_zt16, p, grid2, st);
-    }
-    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
-    if (pl.quad) {
-      if (fast) return launch_sweep_quad_t<true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-      return launch_sweep_quad_t<false, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-    }
-    if (fast) return launch_sweep256_t<true, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-    return launch_sweep256_t<false, 1>(tm_z64, tm_z128, tm_zt16, p, grid2, st);
-  }
-  {
-    CUtensorMap tm_z128;
-    if (int rc = make_tmap_2d_f32(&tm_z128, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, 128, BK)) return rc;
-    if (pl.quad) {
-      if (hy.on) {
-        // the quad clusters first (they need whole groups of 4 SMs inside a GPC), then the pair part on the forked
-        // stream: its few clusters land on the SMs the quad grid left over
-        ForkJoin fj;
-        if (int rc = fj.fork(st)) return rc;
-        BwdParams pp = p;
-        pp.panels = hy.pr.panels; pp.full_items = hy.pr.full_items; pp.split = hy.pr.split; pp.items = hy.pr.items;
-        pp.panel0 = hy.q.panels;
-        const dim3 gridp(2 * hy.pr.pairs, 1, 1);
-        const int rc2 = fast ? launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st)
-                             : launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-        const int rc1 = fast ? launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side)
-                             : launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, pp, gridp, fj.side);
-        const int rc3 = fj.join(st);
-        return rc1 ? rc1 : (rc2 ? rc2 : rc3);
-      }
-      if (fast) return launch_sweep_quad_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-      return launch_sweep_quad_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-    }
-    if (fast) return launch_sweep256_t<true>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-    return launch_sweep256_t<false>(tm_z64, tm_z128, tm_zt, p, grid2, st);
-  }
+  return launch_sweep(L, ws, n_s, n_t, d, kernel_mul, kernel_num, row_begin, row_count, row_begin2, row_count2, finalize,
+                      loss, stats, partial, U, st, false);
 }
 
 int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, const float *grad_out,
@@ -758,26 +780,8 @@ int edrl_mmd_apply_grad(int n_s, int n_t, int d, int flags, const float *stats, 
   EDRL_CHECK_ARG(workspace_bytes >= L.total, "MK_MMD apply_grad: workspace too small");
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n, "MK_MMD apply_grad: bad row range");
   const uint8_t *ws = reinterpret_cast<const uint8_t *>(workspace);
-  const int rows = row_count + row_count2;
-  const HybridPlan hy = make_hybrid(L, row_count, row_count2);
-  const ApplyPlan pa{hy.q.panels, hy.q.full_items, hy.q.split, hy.q.pass_feats};
-  const ApplyPlan pb{hy.pr.panels, hy.pr.full_items, hy.pr.split, hy.pr.pass_feats};
-  const float *zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
-  const float *zlo = L.split3 ? reinterpret_cast<const float *>(ws + L.off_zlo) : nullptr;
-  const double *cs = reinterpret_cast<const double *>(ws + L.off_colsum_hi);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool v4 = (d % 4 == 0) && ((((uintptr_t)U | (uintptr_t)dZ) & 15) == 0);
-  dim3 grid(rows, v4 ? (d + 2047) / 2048 : (d + 511) / 512);
-  if (v4)
-    mmd_apply_grad_kernel<true><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                      row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
-        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
-  else
-    mmd_apply_grad_kernel<false><<<grid, 128, 0, st>>>(U, zhi, zlo, cs, stats, grad_out, row_begin, row_count, row_begin2,
-                                                       row_count2, d, L.d_pad, L.n, L.n_pad, pa, pb,
-        reinterpret_cast<const float *>(ws + L.off_rowsum), dZ);
-  EDRL_LAUNCHED();
-  return 0;
+  return launch_apply(L, ws, d, stats, grad_out, U, row_begin, row_count, row_begin2, row_count2, dZ,
+                      make_hybrid(L, row_count, row_count2), reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -395,389 +395,9 @@ mmd_bwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 }
 
 
-// ----------------------------------------------------------------------------- K3p: CTA-pair backward (TF32)
-// One 2-CTA cluster (an SM pair, tcgen05 cta_group::2) owns a 128-row panel I of Z and 512 feature columns:
-//   S phase   S_IJ = Z_I Z_J^T          M=128 (64 rows per CTA), N=128 (64 rows of J per CTA), K = d
-//   epilogue  each CTA turns its 64 x 128 slice of S into G (TF32) in its own shared memory
-//   P phase   dZ^T[f, i] += Zt[f, j] G[i, j]   M=256 features (128 per CTA), N=128 rows i (the two CTAs' G halves
-//             are the two halves of the B operand -- no exchange), K = 128 columns j
-// so the Gram tile is recomputed once per (I, J) -- not once per 256-column slice of d like mmd_bwd_kernel --
-// and, for d <= 512, the Z_I rows stay resident in shared memory for the whole J loop.  Per J tile each CTA
-// ingests 256 KiB (64 rows of Z_J + its 256 x 128 block of Z^T) instead of 640 KiB: both kernels are bound by
-// the ~11 TB/s the L2 delivers to the SMs (profiles/), so bytes per tile is what sets the time.
+// ----------------------------------------------------------------------------- shared-memory units of the pair sweeps
+// (mmd_sweep.cuh; the separate CTA-pair backward that first used them -- 128-column S tiles, 0.32 of the TF32 roofline --
+//  is gone: edrl_mmd_backward runs the fused sweep and apply_grad in place)
 constexpr int P2_STAGE = 16384;                 // ring stage per CTA
 constexpr int P2_CHUNK = 8192;                  // 64 rows x 32 floats, 128-byte swizzle
-constexpr int P2_ZI_BYTES = 16 * P2_CHUNK;      // 64 rows x 512 floats
-constexpr int P2_G_BYTES = 4 * P2_CHUNK;        // 64 rows x 128 columns j
-constexpr int P2_CTRL_BYTES = 3072;
 constexpr int P2_FEATS = 512;                   // feature columns per pair and pass (2 M-tiles of 256)
-
-// RES = number of 32-column chunks of Z_I kept resident (0: none, d > 512; 8: half of a 512-wide panel -- the
-// other half is re-streamed so that 8 ring stages (128 KiB in flight per SM) still fit; 16 left only 4 stages and
-// was TMA-latency bound).
-template <int RES>
-struct Bwd2Cfg {
-  static constexpr int ZI_BYTES = RES * P2_CHUNK;
-  static constexpr int STAGES = (232448 - ZI_BYTES - P2_G_BYTES - P2_CTRL_BYTES) / P2_STAGE > 11
-                                    ? 11
-                                    : (232448 - ZI_BYTES - P2_G_BYTES - P2_CTRL_BYTES) / P2_STAGE;
-  static constexpr int SMEM_BYTES = ZI_BYTES + P2_G_BYTES + STAGES * P2_STAGE + P2_CTRL_BYTES;
-};
-
-struct Bwd2Ctrl {
-  uint64_t full[12];              // used in the leader CTA only (both CTAs' TMA bytes land here)
-  uint64_t empty[12];             // per CTA, arrived on by the multicast tcgen05.commit
-  uint64_t zi_full;               // leader
-  uint64_t s_full[2];             // per CTA (multicast commit)
-  uint64_t s_empty[2];            // leader, 16 arrivals: 8 epilogue warps x 2 CTAs
-  uint64_t g_full;                // leader, 16 arrivals
-  uint64_t g_empty;               // per CTA (multicast commit)
-  uint64_t dz_full;               // per CTA (multicast commit)
-  uint32_t tmem_base;
-  uint32_t pad;
-  float2 colinfo[2][BN];          // (r_j, a_j) per S stage; re-used for the row-sum exchange after the J loop
-  float negc[MAX_KERNELS];
-  float w[MAX_KERNELS];
-};
-static_assert(sizeof(Bwd2Ctrl) <= P2_CTRL_BYTES, "Bwd2Ctrl does not fit its smem slot");
-static_assert(Bwd2Cfg<0>::SMEM_BYTES <= 232448 && Bwd2Cfg<8>::SMEM_BYTES <= 232448, "smem budget");
-
-// (The fused forward + gradient training pass lives in mmd_sweep256_kernel / mmd_sweep_quad_kernel below; this kernel is
-// the separate backward of edrl_mmd_backward and the independent cross-check of the sweep in the tests.)
-template <bool FAST, int RES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BWD_THREADS, 1)
-mmd_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_constant__ CUtensorMap tm_zt,
-                    const BwdParams p) {
-  using Cfg = Bwd2Cfg<RES>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *zi_smem = smem;
-  uint8_t *g_smem = smem + Cfg::ZI_BYTES;
-  uint8_t *ring = g_smem + P2_G_BYTES;
-  Bwd2Ctrl *ctl = reinterpret_cast<Bwd2Ctrl *>(ring + Cfg::STAGES * P2_STAGE);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = (rank == 0);
-  const int panel = blockIdx.x >> 1;
-  // the panels of row range 1 come first, then those of the optional range 2 (sharded: source rows, target rows)
-  const int np1 = (p.row_count + BM - 1) / BM;
-  const bool second = panel >= np1;
-  const int lpanel = second ? panel - np1 : panel;
-  const int rng_begin = second ? p.row_begin2 : p.row_begin;
-  const int rng_count = second ? p.row_count2 : p.row_count;
-  const int out_row0 = (second ? p.row_count : 0) + lpanel * BM;   // row of dz this panel starts at
-  const int row_base = rng_begin + lpanel * BM;           // first global row of the pair's 128-row panel
-  const int f0 = blockIdx.y * P2_FEATS;                   // first feature column of this pass
-  // gridDim.z splits the column (J) range: slab z sweeps J tiles [J0, J0 + nJ) and writes its own partial output
-  // slab (summed by edrl_mmd_apply_grad).  128 panels on 74 SM pairs are two waves; four slabs make it 1.75.
-  const int J0 = (int)(((long long)blockIdx.z * p.nb) / gridDim.z);
-  const int nJ = (int)(((long long)(blockIdx.z + 1) * p.nb) / gridDim.z) - J0;
-  const int kchunks = p.kchunks;                          // even (d_pad is a multiple of 64)
-  const int ntile = (p.d_pad - f0 > 256) ? 2 : 1;         // M-tiles of 256 features that hold real columns
-  const int nres = (kchunks < RES) ? kchunks : RES;       // resident chunks of Z_I (even)
-
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();           // the swizzled tiles need a 1024-byte aligned base
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&ctl->full[s], 1);
-      mbar_init(&ctl->empty[s], 1);
-    }
-    mbar_init(&ctl->zi_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&ctl->s_full[s], 1);
-      mbar_init(&ctl->s_empty[s], 2 * BWD_EPI_THREADS / 32);
-    }
-    mbar_init(&ctl->g_full, 2 * BWD_EPI_THREADS / 32);
-    mbar_init(&ctl->g_empty, 1);
-    mbar_init(&ctl->dz_full, 1);
-    fence_barrier_init();
-    fence_proxy_async_smem();
-  }
-  if (warp == 1) {
-    tmem_alloc_pair(&ctl->tmem_base, 512);
-    tmem_relinquish_pair();
-  }
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_z64);
-    tma_prefetch_desc(&tm_zt);
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                     // the peer's barriers exist before anything targets them
-  tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
-  const uint32_t tmem_dz = tmem_base;                     // columns [0, 256): two M-tiles of dZ^T
-  const uint32_t tmem_s = tmem_base + 256;                // two S stages of 64 columns (128 x 64 = 64 rows x 128)
-
-  if (warp == 0) {
-    // ===================== TMA producer (both CTAs; bytes are signalled on the leader's barriers) ==========
-    // The whole warp runs this code converged; one elected lane issues (see ptx.cuh, *_elect).
-    {
-      int s = 0;
-      uint32_t ph = 0;
-      const uint32_t full0 = mapa_u32(smem_u32(&ctl->full[0]), 0);        // leader's full[0]; full[s] = + 8 s
-      auto acquire = [&]() -> uint8_t * {
-        mbar_wait(&ctl->empty[s], ph ^ 1);
-        mbar_expect_tx_elect(&ctl->full[s], 2 * P2_STAGE, leader ? 1u : 0u);
-        return ring + s * P2_STAGE;
-      };
-      auto next = [&]() {
-        if (++s == Cfg::STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      };
-      const int irow = row_base + (int)rank * 64;
-      if (RES > 0) {
-        mbar_expect_tx_elect(&ctl->zi_full, 2u * (uint32_t)nres * P2_CHUNK, leader ? 1u : 0u);
-        const uint32_t bar = mapa_u32(smem_u32(&ctl->zi_full), 0);
-        for (int kc = 0; kc < nres; ++kc)
-          tma_load_2d_pair_elect(zi_smem + kc * P2_CHUNK, &tm_z64, bar, kc * BK, irow);
-      }
-      auto load_S = [&](int J) {
-        const int jrow = (J0 + J) * BN + (int)rank * 64;
-        for (int kc = 0; kc < nres; kc += 2) {           // Z_I resident: a stage carries two chunks of Z_J
-          uint8_t *st = acquire();
-          const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * BK, jrow);
-          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, (kc + 1) * BK, jrow);
-          next();
-        }
-        for (int kc = nres; kc < kchunks; ++kc) {        // streamed: a stage carries one chunk of Z_I and of Z_J
-          uint8_t *st = acquire();
-          const uint32_t bar = full0 + 8u * (uint32_t)s;
-          tma_load_2d_pair_elect(st, &tm_z64, bar, kc * BK, irow);
-          tma_load_2d_pair_elect(st + P2_CHUNK, &tm_z64, bar, kc * BK, jrow);
-          next();
-        }
-      };
-      auto load_P = [&](int J) {
-        for (int t = 0; t < ntile; ++t)
-          for (int a4 = 0; a4 < BN / BK; ++a4) {
-            uint8_t *st = acquire();
-            const uint32_t bar = full0 + 8u * (uint32_t)s;
-            tma_load_2d_pair_elect(st, &tm_zt, bar, (J0 + J) * BN + a4 * BK, f0 + t * 256 + (int)rank * 128);
-            next();
-          }
-      };
-      load_S(0);
-      for (int J = 0; J < nJ; ++J) {
-        if (J + 1 < nJ) load_S(J + 1);
-        load_P(J);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: the leader CTA's warp 1 drives both tensor cores =====================
-    if (leader) {
-      constexpr uint32_t idesc_s = make_idesc_tf32(128, BN);      // 64 rows per CTA
-      constexpr uint32_t idesc_p = make_idesc_tf32(256, BN);      // 128 feature rows per CTA
-      int s = 0;
-      uint32_t ph = 0;
-      auto next = [&]() {
-        if (++s == Cfg::STAGES) {
-          s = 0;
-          ph ^= 1;
-        }
-      };
-      const uint32_t ring_addr = smem_u32(ring);
-      const uint32_t zi_addr = smem_u32(zi_smem);
-      const uint32_t g_addr = smem_u32(g_smem);
-      if (RES > 0) {
-        mbar_wait(&ctl->zi_full, 0);
-        tc_fence_after();
-      }
-      auto issue_S = [&](int J) {
-        const int b = J & 1;
-        const uint32_t u = (uint32_t)(J >> 1);
-        mbar_wait_cluster(&ctl->s_empty[b], (u & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_s + b * 64;
-        for (int kc = 0; kc < nres; kc += 2) {           // resident Z_I, two Z_J chunks per stage
-          mbar_wait(&ctl->full[s], ph);
-          tc_fence_after();
-          const uint32_t st = ring_addr + s * P2_STAGE;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint64_t a_d = make_kmajor_sw128_desc(zi_addr + (kc + h) * P2_CHUNK);
-            const uint64_t b_d = make_kmajor_sw128_desc(st + h * P2_CHUNK);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-              mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc + h > 0 || k > 0) ? 1u : 0u);
-            }
-          }
-          mma_commit_pair_elect(&ctl->empty[s]);
-          next();
-        }
-        for (int kc = nres; kc < kchunks; ++kc) {        // streamed Z_I chunk + Z_J chunk
-          mbar_wait(&ctl->full[s], ph);
-          tc_fence_after();
-          const uint32_t st = ring_addr + s * P2_STAGE;
-          const uint64_t a_d = make_kmajor_sw128_desc(st);
-          const uint64_t b_d = make_kmajor_sw128_desc(st + P2_CHUNK);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-            mma_tf32_ss_pair_elect(d_tmem, a_d + adv, b_d + adv, idesc_s, (kc > 0 || k > 0) ? 1u : 0u);
-          }
-          mma_commit_pair_elect(&ctl->empty[s]);
-          next();
-        }
-        mma_commit_pair_elect(&ctl->s_full[b]);
-      };
-      auto issue_P = [&](int J) {
-        mbar_wait_cluster(&ctl->g_full, (uint32_t)(J & 1));
-        tc_fence_after();
-        for (int t = 0; t < ntile; ++t)
-          for (int a4 = 0; a4 < BN / BK; ++a4) {
-            mbar_wait(&ctl->full[s], ph);
-            tc_fence_after();
-            const uint64_t a_d = make_kmajor_sw128_desc(ring_addr + s * P2_STAGE);
-            const uint64_t b_d = make_kmajor_sw128_desc(g_addr + a4 * P2_CHUNK);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
-              mma_tf32_ss_pair_elect(tmem_dz + t * BN, a_d + adv, b_d + adv, idesc_p,
-                                     (J > 0 || a4 > 0 || k > 0) ? 1u : 0u);
-            }
-            mma_commit_pair_elect(&ctl->empty[s]);
-            next();
-          }
-        mma_commit_pair_elect(&ctl->g_empty);
-      };
-      issue_S(0);
-      for (int J = 0; J < nJ; ++J) {
-        if (J + 1 < nJ) issue_S(J + 1);
-        issue_P(J);
-      }
-      mma_commit_pair_elect(&ctl->dz_full);
-    }
-  } else {
-    // ===================== epilogue (both CTAs): S -> G for this CTA's 64 rows =====================
-    const int ew = warp - 2;
-    const int lg = warp & 3;                 // TMEM lane group of this warp
-    const int ch = ew >> 2;                  // which 32 of the S stage's 64 TMEM columns
-    const int et = ew * 32 + lane;
-    const int tl = lg * 32 + lane;           // TMEM lane
-    const int r = tl & 63;                   // row of this CTA's 64-row slice
-    const int jh = tl >> 6;                  // lanes 64..127 hold columns 64..127 of the same rows (2x2 layout)
-    const int j0 = jh * 64 + ch * 32;        // first of this thread's 32 columns inside the J tile
-    const int gi = row_base + (int)rank * 64 + r;
-
-    const float sigma0 = p.stats[EDRL_MMD_STAT_SIGMA0];
-    const float cval = p.stats[EDRL_MMD_STAT_C];
-    float sig_last = sigma0;
-    for (int k = 0; k < p.num - 1; ++k) sig_last *= p.mul;
-    const float negc_last = -LOG2E / sig_last;
-    if (!FAST && et == 0) fill_generic_coefs(ctl->negc, ctl->w, sigma0, p.mul, p.num);
-
-    const float ri = (gi < p.n_pad) ? (float)p.racc[gi] : 0.f;
-    const float ai = (gi < p.n_pad) ? p.a[gi] : 0.f;
-    const float nai_sig = -ai / sigma0;
-    const uint32_t g_full_leader = mapa_u32(smem_u32(&ctl->g_full), 0);
-    float rowsum = 0.f;
-
-    for (int J = 0; J < nJ; ++J) {
-      const int b = J & 1;
-      const uint32_t u = (uint32_t)(J >> 1);
-      if (et < BN) {
-        const int gj = (J0 + J) * BN + et;
-        ctl->colinfo[b][et] = make_float2((float)p.racc[gj], p.a[gj]);
-      }
-      named_barrier_sync(1, BWD_EPI_THREADS);
-      mbar_wait(&ctl->s_full[b], u & 1);
-      tc_fence_after();
-      mbar_wait(&ctl->g_empty, (uint32_t)((J & 1) ^ 1));     // P(J-1) has consumed the G buffer
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_s + ((uint32_t)(lg * 32) << 16) + (uint32_t)(b * 64 + ch * 32), v);
-      tmem_ld_wait();
-      float g[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float2 ci = ctl->colinfo[b][j0 + j];
-        const float Lraw = fmaf(-2.f, __uint_as_float(v[j]), ri + ci.x);
-        const float L = fmaxf(Lraw, 0.f);
-        float K, Q;
-        kernel_terms<FAST>(L, negc_last, ctl->negc, ctl->w, p.num, K, Q);
-        float gv = fmaf(ci.y * Q, nai_sig, (ci.y != 0.f) ? cval : 0.f);   // a_j == 0 <=> padded column
-        gv = (Lraw >= 0.f) ? gv : 0.f;
-        const float gh = to_tf32(gv);
-        g[j] = gh;
-        rowsum += gh;
-      }
-      // this thread's 32 values of row r go to K-atom (j0 / 32) of the B operand, 128-byte swizzle
-      uint8_t *atom = g_smem + (j0 >> 5) * P2_CHUNK + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)
-        *reinterpret_cast<float4 *>(atom + ((q4 ^ (r & 7)) << 4)) =
-            make_float4(g[q4 * 4 + 0], g[q4 * 4 + 1], g[q4 * 4 + 2], g[q4 * 4 + 3]);
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(g_full_leader);
-        mbar_arrive_cluster(mapa_u32(smem_u32(&ctl->s_empty[b]), 0));
-      }
-    }
-    // ---- row sums of G: 4 partials per row (2 column halves x 2 lane halves) -> all 128 rows in both CTAs ----
-    named_barrier_sync(1, BWD_EPI_THREADS);                  // everyone is done with colinfo
-    float *part = reinterpret_cast<float *>(&ctl->colinfo[0][0]);   // [4][64]
-    float *rs_all = reinterpret_cast<float *>(&ctl->colinfo[1][0]); // [128]
-    part[(jh * 2 + ch) * 64 + r] = rowsum;
-    named_barrier_sync(1, BWD_EPI_THREADS);
-    if (et < 64) {
-      const float tot = (part[et] + part[64 + et]) + (part[128 + et] + part[192 + et]);
-      rs_all[rank * 64 + et] = tot;
-      st_cluster_f32(mapa_u32(smem_u32(&rs_all[rank * 64 + et]), rank ^ 1u), tot);
-    }
-  }
-  __syncwarp();
-  cluster_sync_all();                                        // row sums exchanged (DSMEM writes visible)
-
-  if (warp >= 2) {
-    // ===================== write-out: dZ[i, f] = coef (rowsum_i z_i[f] - dZ^T[f, i]) =====================
-    const int ew = warp - 2;
-    const int lg = warp & 3;
-    const int ch = ew >> 2;
-    const int tl = lg * 32 + lane;                           // feature lane of the M-tile
-    const float *rs_all = reinterpret_cast<const float *>(&ctl->colinfo[1][0]);
-    const float M = p.stats[EDRL_MMD_STAT_M];
-    const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
-    const float coef = 4.f * sgn * p.grad_out[0];
-    int rows_here = rng_count - lpanel * BM;
-    if (rows_here > BM) rows_here = BM;
-    if (p.n - row_base < rows_here) rows_here = p.n - row_base;
-    mbar_wait(&ctl->dz_full, 0);
-    tc_fence_after();
-    for (int t = 0; t < ntile; ++t) {
-      const int f = f0 + t * 256 + (int)rank * 128 + tl;
-      const bool f_ok = f < p.d;
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int i0 = ch * 64 + c2 * 32;
-        if (i0 >= rows_here) break;                          // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_dz + ((uint32_t)(lg * 32) << 16) + (uint32_t)(t * BN + i0), v);
-        tmem_ld_wait();
-        if (f_ok) {
-          const float *zc = p.zhi + (size_t)(row_base + i0) * p.d_pad + f;
-          float *oc = p.dz + ((size_t)blockIdx.z * (size_t)(p.row_count + p.row_count2) + out_row0 + i0) * p.d + f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (i0 + j < rows_here)
-              oc[(size_t)j * p.d] = coef * fmaf(rs_all[i0 + j], zc[(size_t)j * p.d_pad], -__uint_as_float(v[j]));
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                                        // nobody exits while the peer may still touch it
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
-  }
-}
-

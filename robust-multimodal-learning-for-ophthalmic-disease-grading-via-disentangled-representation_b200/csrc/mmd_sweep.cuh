@@ -1207,11 +1207,11 @@ struct ApplyPlan {                // the part of a SweepPlan edrl_mmd_apply_grad
 // one block row per output row (no per-element division), 128-bit accesses when d % 4 == 0
 template <bool VEC4>
 __global__ void __launch_bounds__(128)
-mmd_apply_grad_kernel(const float *__restrict__ U, const float *__restrict__ zhi, const float *__restrict__ zlo,
+mmd_apply_grad_kernel(const float *U, const float *__restrict__ zhi, const float *__restrict__ zlo,
                       const double *__restrict__ colsum_hi,
                       const float *__restrict__ stats, const float *__restrict__ grad_out, int row_begin, int row_count,
                       int row_begin2, int row_count2, int d, int d_pad, int n, int n_pad, ApplyPlan pa, ApplyPlan pb,
-                      const float *__restrict__ rowsum, float *__restrict__ dz) {
+                      const float *__restrict__ rowsum, float *dz) {     // (U may be dz: edrl_mmd_backward)
   const float M = stats[EDRL_MMD_STAT_M];
   const float sgn = (M > 0.f) ? 1.f : ((M < 0.f) ? -1.f : 0.f);
   const float coef = 4.f * sgn * grad_out[0];

@@ -672,3 +672,25 @@ def test_hybrid_quad_plus_pair_launch_matches_the_single_launch(tmp_path, ns, nt
     tol = dict((m[0], m) for m in MODES)["tf32"]
     assert np.isclose(float(b["loss"]), want, rtol=tol[2], atol=1e-6)
     assert np.abs(b["gx"] - gx).max() <= tol[3] * max(np.abs(gx).max(), np.abs(gy).max())
+
+
+def test_separate_backward_is_the_first_call_of_the_autograd_thread(tmp_path):
+    """`EDRL_MMD_FUSED=0` (and 3xTF32 at d > 768): `edrl_mmd_backward` builds tensor maps, and in a fresh process it is the
+    first call this library sees on torch's autograd thread -- which has a device selected but possibly no context bound
+    (cuTensorMapEncodeTiled: CUDA_ERROR_INVALID_CONTEXT before the device guard bound one)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "import edrl_b200\n"
+        "for prec, d in (('tf32', 8), ('3xtf32', 8), ('3xtf32', 800)):\n"
+        "    x = torch.randn(6, d, device='cuda', requires_grad=True)\n"
+        "    y = torch.randn(5, d, device='cuda', requires_grad=True)\n"
+        "    edrl_b200.MK_MMD(x, y, precision=prec).backward()\n"
+        "    assert torch.isfinite(x.grad).all() and x.grad.abs().sum() > 0\n"
+        "print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, EDRL_MMD_FUSED="0"), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
