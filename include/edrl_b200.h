@@ -102,7 +102,7 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                       int row_begin, int row_count, float *dZ,
                       void *workspace, size_t workspace_bytes, void *stream);
 
-/* Fused training pass (TF32 / TF32H / F16S): forward block sums AND the bandwidth-independent part of the gradient in one
+/* Fused training pass (every precision mode): forward block sums AND the bandwidth-independent part of the gradient in one
  * sweep over the Gram tiles of rows [row_begin, row_begin + row_count) -- a training step then visits every tile
  * once instead of 1.5 times (edrl_mmd_forward + edrl_mmd_backward).  Same math as code/MMD.py:16-72 + autograd:
  *   U[i, :] = -(G' Z)_i,  G'_ij = -a_i a_j Q_ij / sigma_0;  rowsum(G')_i goes to the workspace (apply_grad adds

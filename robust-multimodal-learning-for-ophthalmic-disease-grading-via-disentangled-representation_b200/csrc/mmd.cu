@@ -5,8 +5,7 @@
 //   mmd_fwd.cuh    K2   loss-only forward: persistent, warp-specialised TMA -> smem ring -> tcgen05.mma (kind::tf32) ->
 //                       TMEM -> fused distance / exp-sum / block-reduce epilogue over upper-triangular tiles
 //                       (mmd_fwd_pair_kernel: 256 x 256 tiles, cta_group::2; mmd_fwd_kernel: 128 x 128, 3xTF32, K matrix)
-//   mmd_bwd.cuh    K3   the first tile-recomputing backward (mmd_bwd_kernel: 3xTF32 beyond the fused sweep, A/B runs); the
-//                       TF32-family edrl_mmd_backward runs the sweep + apply_grad in place
+//   mmd_bwd.cuh         BwdParams, shared-memory units (edrl_mmd_backward runs the sweep + apply_grad in place)
 //   mmd_sweep.cuh  K3q  the training path: fused forward sums + gradient in one persistent sweep over the Gram tiles
 //                       (mmd_sweep256_kernel: CTA pairs; mmd_sweep_quad_kernel: 4-CTA clusters for d > 768) and
 //                       mmd_apply_grad_kernel
@@ -305,20 +304,6 @@ static int forward_impl(int mode, const float *X, const float *Y, int n_s, int n
   return launch_fwd<MODE_GRAM>(L.split3, fast, tm_hi, tm_lo, p, grid, st);
 }
 
-template <bool SPLIT3, bool FAST>
-static int launch_bwd_t(const CUtensorMap &a, const CUtensorMap &b, const CUtensorMap &c, const CUtensorMap &d4,
-                        const BwdParams &p, dim3 grid, cudaStream_t st) {
-  using Cfg = BwdCfg<SPLIT3>;
-  auto kern = mmd_bwd_kernel<SPLIT3, FAST>;
-  // per launch (cheap): the attribute is per device, a process may drive several
-  EDRL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  kern<<<grid, BWD_THREADS, Cfg::SMEM_BYTES, st>>>(a, b, c, d4, p);
-  EDRL_LAUNCHED();
-  return 0;
-}
-
-
-
 #include "mmd_sweep.cuh"
 
 template <bool FAST, int MODE = 0>
@@ -387,7 +372,8 @@ static int quad_clusters_resident() {
 static bool quad_wanted(const Layout &L) {
   static const bool no_quad = (getenv("EDRL_MMD_QUAD") != nullptr && atoi(getenv("EDRL_MMD_QUAD")) == 0);   // A/B runs
   // (up to 768 columns the second pair would hold one 256-column tile or less: two pair passes are faster)
-  return L.d_pad > P2_FEATS + P2_FEATS / 2 && !no_quad;
+  // (3xTF32 has no quad variant: the pair kernel sweeps the Gram once per 512-column pass)
+  return L.d_pad > P2_FEATS + P2_FEATS / 2 && !no_quad && !L.split3;
 }
 
 // force_kind: -1 = by width, 0 = pair kernel, 1 = quad kernel; clusters_override: persistent clusters available (hybrid)
@@ -691,46 +677,12 @@ int edrl_mmd_backward(int n_s, int n_t, int d, float kernel_mul, int kernel_num,
                  "MK_MMD backward: row range [%d, %d) outside [0, %d)", row_begin, row_begin + row_count, L.n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-  CUtensorMap tm_hi, tm_lo, tm_thi, tm_tlo;
-  if (int rc = make_tmap_2d_f32(&tm_hi, ws + L.off_zhi, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
-  if (int rc = make_tmap_2d_f32(&tm_thi, ws + L.off_zthi, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, DC, BK)) return rc;
-  if (L.split3) {
-    if (int rc = make_tmap_2d_f32(&tm_lo, ws + L.off_zlo, L.n_pad, L.d_pad, (uint64_t)L.d_pad * 4, BM, BK)) return rc;
-    if (int rc = make_tmap_2d_f32(&tm_tlo, ws + L.off_ztlo, L.d_pad, L.n_pad, (uint64_t)L.n_pad * 4, DC, BK))
-      return rc;
-  } else {
-    tm_lo = tm_hi;
-    tm_tlo = tm_thi;
-  }
-  BwdParams p;
-  p.n = L.n; p.n_s = n_s; p.n_pad = L.n_pad; p.d = d; p.d_pad = L.d_pad;
-  p.nb = L.n_pad / BN; p.kchunks = L.d_pad / BK; p.num = kernel_num; p.mul = kernel_mul;
-  p.row_begin = row_begin; p.row_count = row_count;
-  p.racc = reinterpret_cast<const double *>(ws + L.off_r);
-  p.a = reinterpret_cast<const float *>(ws + L.off_a);
-  p.zhi = reinterpret_cast<const float *>(ws + L.off_zhi);
-  p.zlo = reinterpret_cast<const float *>(ws + L.off_zlo);
-  p.stats = stats; p.grad_out = grad_out; p.dz = dZ;
-  p.acc = nullptr; p.ticket = nullptr; p.partial = nullptr; p.loss = nullptr; p.stats_out = nullptr;
-  p.n_t = n_t; p.finalize = 0; p.row_begin2 = 0; p.row_count2 = 0; p.fscale = nullptr;
-  p.panel0 = 0; p.ticket_total = 0; p.s_ahead = 0;
-  const bool fast = (kernel_mul == 2.0f && kernel_num == 5);
-  static const bool legacy = (getenv("EDRL_MMD_BWD_LEGACY") != nullptr);   // A/B switch for profiling
-  if (!L.split3 && !legacy) {
-    // TF32 and its binary16-container modes: the fused sweep (its forward sums are a by-product nobody reads here) writes
-    // U into dZ, apply_grad finishes it in place -- one U slab, hence the single-launch plan
-    if (int rc = launch_sweep(L, ws, n_s, n_t, d, kernel_mul, kernel_num, row_begin, row_count, 0, 0, 0, nullptr, nullptr,
-                              nullptr, dZ, st, true))
-      return rc;
-    return launch_apply(L, ws, d, stats, grad_out, dZ, row_begin, row_count, 0, 0, dZ, single_plan(L, row_count, 0), st);
-  }
-  dim3 grid((row_count + BM - 1) / BM, (d + DC - 1) / DC);
-  if (L.split3) {
-    if (fast) return launch_bwd_t<true, true>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
-    return launch_bwd_t<true, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
-  }
-  if (fast) return launch_bwd_t<false, true>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
-  return launch_bwd_t<false, false>(tm_hi, tm_lo, tm_thi, tm_tlo, p, grid, st);
+  // every precision mode: the fused sweep (its forward sums are a by-product nobody reads here) writes U into dZ,
+  // apply_grad finishes it in place -- one U slab, hence the single-launch plan
+  if (int rc = launch_sweep(L, ws, n_s, n_t, d, kernel_mul, kernel_num, row_begin, row_count, 0, 0, 0, nullptr, nullptr,
+                            nullptr, dZ, st, true))
+    return rc;
+  return launch_apply(L, ws, d, stats, grad_out, dZ, row_begin, row_count, 0, 0, dZ, single_plan(L, row_count, 0), st);
 }
 
 int edrl_mmd_grad_slabs(int n_s, int n_t, int d, int flags, int row_count, int row_count2) {
@@ -755,8 +707,6 @@ int edrl_mmd_forward_grad(const float *X, const float *Y, int n_s, int n_t, int 
   EDRL_DEVICE_GUARD();
   EDRL_CHECK_ARG(X && Y && U, "MK_MMD forward_grad: null argument");
   Layout L = make_layout(n_s, n_t, d, flags);
-  EDRL_CHECK_ARG(!L.split3 || L.d_pad <= P2_FEATS + P2_FEATS / 2,
-                 "MK_MMD forward_grad: the fused 3xTF32 pass covers d <= 768 (d = %d): use the separate kernels", d);
   if (int rc = check_common(n_s, n_t, d, kernel_mul, kernel_num, L, workspace, workspace_bytes)) return rc;
   EDRL_CHECK_ARG(row_begin >= 0 && row_count > 0 && row_begin + row_count <= L.n,
                  "MK_MMD forward_grad: row range [%d, %d) outside [0, %d)", row_begin, row_begin + row_count, L.n);

@@ -4,8 +4,8 @@
 ``MK_MMD(source, target, kernel_mul=2.0, kernel_num=5)`` is a ``torch.autograd.Function`` whose
 forward is one fused tcgen05 pass (the n x n kernel matrix never reaches HBM) and whose backward
 recomputes the kernel tiles.  Arithmetic: Gram on the tensor cores in TF32 (``"tf32"``) or as a
-hi/lo split with three MMAs per product (``"3xtf32"``, fp32-level accuracy; fused forward+gradient
-sweep for d <= 768, the separate first-generation kernels above); everything else fp32 with fp64
+hi/lo split with three MMAs per product (``"3xtf32"``, fp32-level accuracy; the same fused
+forward+gradient sweep, one Gram pass per 512 feature columns); everything else fp32 with fp64
 block accumulators.
 """
 from __future__ import annotations
@@ -26,13 +26,11 @@ FLAG_F16S = 4
 # "f16s": like "tf32h", and the Gram of the fused sweep reads a binary16 copy of the same TF32-rounded operand (one
 # power-of-two scale for the whole matrix): identical significands and exact products, both contractions on kind::f16.
 _PRECISIONS = {"tf32": FLAG_TF32, "3xtf32": FLAG_3XTF32, "tf32h": FLAG_TF32H, "f16s": FLAG_F16S}
-_FUSED_FLAGS = (FLAG_TF32, FLAG_TF32H, FLAG_F16S)
-_FUSED_3X_MAX_D = 768      # the fused 3xTF32 sweep is the CTA-pair kernel (d_pad <= 768); wider inputs take the separate kernels
 
 
 def _fused(flags, d):
     """Does a training step (gradients requested) of this precision and width take the fused forward+gradient sweep?"""
-    return _FUSED and (flags in _FUSED_FLAGS or (flags == FLAG_3XTF32 and d <= _FUSED_3X_MAX_D))
+    return _FUSED        # (every precision mode; 3xTF32 beyond d = 768 sweeps the Gram once per 512-column pass)
 _default_precision = os.environ.get("EDRL_MMD_PRECISION", "tf32").lower()
 NUM_STATS = 8
 # TF32 training steps use the fused pass (forward sums + gradient in one sweep over the Gram tiles);

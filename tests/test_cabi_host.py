@@ -56,7 +56,7 @@ def test_workspace_bytes_is_pure_host_logic(pkg):
     (64, 64, 3072, 128, 0, 148),           # the reference's training shape: 1 panel x 6 feature passes
     (300, 212, 700, 512, 0, 148), (5000, 4600, 700, 9600, 0, 148), (1000, 24, 96, 1024, 0, 132),
     (37, 53, 24, 17, 40, 148), (8192, 8192, 512, 16384, 0, 2)])
-@pytest.mark.parametrize("flags", [0, 2, 4])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4])
 def test_sweep_work_list_covers_every_tile_once(pkg, ns, nt, d, rc, rc2, sms, flags):
     """Host logic of the fused sweep (csrc/mmd.cu make_plan / sweep_item): every (virtual panel, column group) is swept
     by exactly one work item, slabs are non-empty, the slab count is what edrl_mmd_grad_slabs reports, and splitting
@@ -67,7 +67,7 @@ def test_sweep_work_list_covers_every_tile_once(pkg, ns, nt, d, rc, rc2, sms, fl
     assert lib.edrl_mmd_sweep_plan(ns, nt, d, flags, rc, rc2, sms, plan) == 0
     panels, vpanels, full, split, items, pairs, groups, d_pad, quad, pass_feats = list(plan)
     assert panels == -(-rc // 128) + -(-rc2 // 128)
-    assert quad == (1 if d_pad > 768 else 0) and pass_feats == (1024 if quad else 512)
+    assert quad == (1 if d_pad > 768 and flags != 1 else 0) and pass_feats == (1024 if quad else 512)   # (3xTF32: pairs only)
     assert vpanels == panels * -(-d_pad // pass_feats) and d_pad >= d and d_pad % (128 if flags == 4 else 64) == 0
     assert split in (1, 2, 4, 8) and split <= max(groups, 1)
     assert items == full + (vpanels - full) * split and 1 <= pairs <= max(sms // (4 if quad else 2), 1) and pairs <= items

@@ -404,7 +404,7 @@ def test_fused_pass_matches_separate_kernels_and_oracle(raw, ns, nt, d):
 
 
 @pytest.mark.parametrize("ns,nt,d", [(5000, 4600, 700), (3000, 2500, 1100), (9600, 9400, 300)])
-@pytest.mark.parametrize("prec,flag", [("tf32", 0), ("tf32h", 2), ("f16s", 4)])
+@pytest.mark.parametrize("prec,flag", [("tf32", 0), ("tf32h", 2), ("f16s", 4), ("3xtf32", 1)])
 def test_work_list_shapes_fused_vs_separate_kernels(raw, ns, nt, d, prec, flag):
     """Shapes whose work list mixes whole panels, column slabs and several 512-column feature passes (two passes at
     d = 700, three at 1100; 150 / 129 / 149 virtual panels on 74 SM pairs): the persistent fused sweep against the
@@ -694,3 +694,30 @@ def test_separate_backward_is_the_first_call_of_the_autograd_thread(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, EDRL_MMD_FUSED="0"), capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("ns,nt,d", [(700, 650, 1100), (300, 280, 3072)])
+def test_3xtf32_beyond_768_columns_vs_oracle(ns, nt, d):
+    """3xTF32 at d > 768 (the reference's own feature width is 3072): the fused pair sweep, one Gram pass per 512 feature
+    columns, at the fp32-level tolerances of the mode -- forward + backward through the public API, and the separate
+    forward / backward entry points (EDRL_MMD_FUSED=0 takes those) through the C-ABI."""
+    import edrl_b200
+    from gpu_util import RawMMD
+    name, flag, ltol, gtol = MODES[0] if MODES[0][0] == "3xtf32" else [m for m in MODES if m[0] == "3xtf32"][0]
+    rng = np.random.default_rng(ns + d)
+    x = rng.standard_normal((ns, d)).astype(np.float32)
+    y = (rng.standard_normal((nt, d)) * 1.2 + 0.1).astype(np.float32)
+    xt, yt = dev(x).requires_grad_(True), dev(y).requires_grad_(True)
+    loss = edrl_b200.MK_MMD(xt, yt, precision="3xtf32")
+    loss.backward()
+    ref, _, dx, dy = O.mk_mmd_grad(x.astype(np.float64), y.astype(np.float64))
+    assert np.isclose(loss.item(), ref, rtol=ltol, atol=1e-6), (loss.item(), ref)
+    gm = max(np.abs(dx).max(), np.abs(dy).max())
+    assert np.abs(xt.grad.cpu().numpy() - dx).max() <= gtol * gm
+    assert np.abs(yt.grad.cpu().numpy() - dy).max() <= gtol * gm
+    raw = RawMMD()
+    loss0, stats0, _, ws0 = raw.forward(xt.detach(), yt.detach(), flags=flag)
+    dz0 = raw.backward(ns, nt, d, stats0, ws0, 0, ns + nt, grad_out=1.0, flags=flag)
+    torch.cuda.synchronize()
+    assert np.isclose(loss0.item(), ref, rtol=ltol, atol=1e-6)
+    assert np.abs(dz0.cpu().numpy() - np.concatenate([dx, dy])).max() <= gtol * gm
