@@ -637,6 +637,19 @@ cg.replay()
 torch.cuda.synchronize()
 out["graph_loss"] = l2.item()
 out["graph_gx"] = xs.grad.cpu().numpy()
+# two row ranges in one call (a rank's source rows and target rows): the row-block sharded entry on a 1-rank group
+import os, torch.distributed as dist
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 300))
+dist.init_process_group("nccl", rank=0, world_size=1)
+x2, y2 = x.detach().clone().requires_grad_(True), y.detach().clone().requires_grad_(True)
+l3 = edrl_b200.sharded_MK_MMD(x2, y2, precision="tf32")
+l3.backward()
+torch.cuda.synchronize()
+out["two_range_loss"] = l3.item()
+out["two_range_gx"] = x2.grad.cpu().numpy()
+out["two_range_gy"] = y2.grad.cpu().numpy()
+dist.destroy_process_group()
 np.savez(sys.argv[2], **out)
 """
 
@@ -650,20 +663,31 @@ def test_hybrid_quad_plus_pair_launch_matches_the_single_launch(tmp_path, ns, nt
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
-    for mode in ("0", "2"):
+    # "2r": most panels to the pair kernel (its part then starts before the second row range does)
+    for mode in ("0", "2", "2r"):
         path = str(tmp_path / f"h{mode}.npz")
-        env = dict(os.environ, EDRL_MMD_HYBRID=mode)
+        env = dict(os.environ, EDRL_MMD_HYBRID=mode[0])
+        if mode == "2r":
+            env["EDRL_MMD_HYBRID_RATIO"] = "0.05"
         r = subprocess.run([sys.executable, "-c", _HYBRID_CHILD, root, path, str(ns), str(nt), str(d)], env=env,
                            capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         res[mode] = np.load(path)
-    a, b = res["0"], res["2"]
+    a, b, c = res["0"], res["2"], res["2r"]
+    assert abs(float(c["loss"]) - float(a["loss"])) <= 2e-6 * max(1.0, abs(float(a["loss"])))
+    assert np.abs(c["gx"] - a["gx"]).max() <= 2e-5 * float(np.abs(a["gx"]).max())
+    assert np.abs(c["gy"] - a["gy"]).max() <= 2e-5 * float(np.abs(a["gy"]).max())
     gmax = float(np.abs(a["gx"]).max())
     assert abs(float(a["loss"]) - float(b["loss"])) <= 2e-6 * max(1.0, abs(float(a["loss"])))
     assert np.abs(a["gx"] - b["gx"]).max() <= 2e-5 * gmax          # same products, different summation order of the slabs
     assert np.abs(a["gy"] - b["gy"]).max() <= 2e-5 * float(np.abs(a["gy"]).max())
     assert abs(float(b["graph_loss"]) - float(b["loss"])) <= 1e-6
     assert np.abs(b["graph_gx"] - b["gx"]).max() <= 2e-5 * gmax
+    # the two-range call (source rows, then target rows: the second range starts in the middle of the panel list)
+    for r in (a, b, c):
+        assert abs(float(r["two_range_loss"]) - float(a["loss"])) <= 2e-6 * max(1.0, abs(float(a["loss"])))
+        assert np.abs(r["two_range_gx"] - a["gx"]).max() <= 2e-5 * gmax
+        assert np.abs(r["two_range_gy"] - a["gy"]).max() <= 2e-5 * float(np.abs(a["gy"]).max())
     # and against the fp64 oracle
     g = torch.Generator(device="cuda").manual_seed(99)
     x = torch.randn(ns, d, device="cuda", generator=g)
