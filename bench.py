@@ -384,8 +384,8 @@ def select_roofline(peaks):
     import edrl_b200
     out = {"bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s",
            "peak_source": f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json)",
-           "kernel": "topk_sift_kernel<6, true, 3, 8, SORTED> (one warp per row: sample pivot -> survivors -> exact select)",
-           "traffic": profiled_traffic("topk_sift_kernel"),
+           "kernel": "topk_sift_kernel<6, true, 3, 8, SORTED, Rows, 10> (one warp per row: sample pivot -> survivors -> exact select)",
+           "traffic": profiled_traffic("topk_sift_kernel<6, 1, 3, 8, 0"),
            "traffic_note": "DRAM bytes per launch of the unsorted 2^18 x 800 select (ncu --set full, profiles/)"}
     R, W, k = 1 << 18, 800, 100
     x = torch.randn(R, W, device="cuda")

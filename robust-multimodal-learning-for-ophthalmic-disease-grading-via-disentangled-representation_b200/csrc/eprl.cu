@@ -1849,30 +1849,36 @@ static int launch_topk(const Rows &rows, int R, int Wmax, int k, float *vals, in
   static const bool legacy = (getenv("EDRL_TOPK_LEGACY") != nullptr);    // A/B switch for profiling
   static const bool novec = (getenv("EDRL_TOPK_VEC") != nullptr && atoi(getenv("EDRL_TOPK_VEC")) == 0);
   static const bool nosift = (getenv("EDRL_TOPK_SIFT") != nullptr && atoi(getenv("EDRL_TOPK_SIFT")) == 0);
-  // rows from this width on take the streaming sift kernel (80 registers, 6 blocks per SM) instead of the resident one,
-  // whose row in registers costs occupancy from W = 1600 on (128 registers, 4 blocks per SM)
+  // rows from this width on take the streaming sift kernel instead of the resident one (A/B runs; with the resident
+  // kernel compiled for 6-8 blocks per SM it is the faster one up to its limit of 2048 columns)
   static const int stream_minw = getenv("EDRL_TOPK_STREAM_MINW") ? atoi(getenv("EDRL_TOPK_STREAM_MINW")) : 2049;
   if (uniform && Wmax >= 512 && Wmax <= 2048 && Wmax < stream_minw && k <= 128 && !legacy && !novec && !nosift && rows.vec4_ok()) {
     // sift select (topk_sift.cuh): sample pivot -> survivors -> exact select, when the sampling plan fits the list
     const int W4 = Wmax >> 2;
     bool done = false;
-#define EDRL_SIFT_CASE(FI_, P_, SSTR_, SL_)                                                                          \
+#define EDRL_SIFT_CASE(FI_, P_, SSTR_, SL_, BLK_)                                                                    \
   if (!done && W4 / 32 == FI_ && ((W4 % 32) != 0) == P_) {                                                           \
     const SiftPlan sp = sift_plan(Wmax, k, 32 * ((FI_ * 4 + SSTR_ - 1) / SSTR_), 32 * SL_);                         \
     if (sp.ok) {                                                                                                      \
       const int grid = (R + 3) / 4;                                                                                   \
       if (sorted)                                                                                                     \
-        topk_sift_kernel<FI_, P_, SSTR_, SL_, true, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+        topk_sift_kernel<FI_, P_, SSTR_, SL_, true, Rows, BLK_><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
       else                                                                                                            \
-        topk_sift_kernel<FI_, P_, SSTR_, SL_, false, Rows><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
+        topk_sift_kernel<FI_, P_, SSTR_, SL_, false, Rows, BLK_><<<grid, 128, 0, st>>>(rows, R, Wmax, k, sp.jtarget, vals, idx); \
       done = true;                                                                                                    \
     }                                                                                                                 \
   }
-    EDRL_SIFT_CASE(4, false, 1, 8)       // W = 512
-    EDRL_SIFT_CASE(6, true, 3, 8)        // W = 800 (the reference's S): 8 sample values per lane
-    EDRL_SIFT_CASE(8, false, 2, 8)       // W = 1024
-    EDRL_SIFT_CASE(12, true, 2, 8)       // W = 1600 (C = 3 negatives)
-    EDRL_SIFT_CASE(16, false, 2, 8)      // W = 2048
+    // BLK_: resident blocks per SM the kernel is compiled for (launch bounds -> registers per thread).  The kernel is bound
+    // by the latency of its per-row scan / histogram-walk chains (38 % of the stall samples: short scoreboard), so it
+    // wants warps, not registers -- measured, unsorted / sorted % of HBM: W = 800 with 8 | 10 | 12 blocks 65.7 / 43.2 |
+    // 69.7 / 44.1 | 64.2 / 42.0 (40 registers spill); W = 1024 with 4 | 7 | 9 blocks 62.4 / 44.4 | 71.8 / 49.1 | 77.5 /
+    // 51.0; W = 1600 with 4 | 6 | 8 blocks 64.5 / 50.3 | 77.1 / 58.1 | 83.5 / 59.2; W = 2048 with 4 | 6 blocks 71.1 / 56.2 |
+    // 84.7 / 64.0; W = 512 with 8 | 12 | 16 blocks 51.7 | 53.9 | 48.7
+    EDRL_SIFT_CASE(4, false, 1, 8, 12)      // W = 512
+    EDRL_SIFT_CASE(6, true, 3, 8, 10)       // W = 800 (the reference's S): 8 sample values per lane
+    EDRL_SIFT_CASE(8, false, 2, 8, 9)       // W = 1024
+    EDRL_SIFT_CASE(12, true, 2, 8, 8)       // W = 1600 (C = 3 negatives)
+    EDRL_SIFT_CASE(16, false, 2, 8, 6)      // W = 2048
 #undef EDRL_SIFT_CASE
     if (done) {
       EDRL_LAUNCHED();
