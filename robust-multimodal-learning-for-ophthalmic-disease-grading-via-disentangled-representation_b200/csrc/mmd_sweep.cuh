@@ -12,6 +12,7 @@
 constexpr int Q_GROUP = 256;                   // columns per S group
 constexpr int Q_G_BYTES = 8 * P2_CHUNK;        // 64 rows x 256 columns j
 constexpr int Q_CTRL_BYTES = 8192;
+constexpr int Q_CTRL_SHORT_BYTES = 3072;       // 3xTF32: the control block up to and including its first column buffers
 constexpr int SW_EPI_WARPS = 16;               // 4 per TMEM lane group: one 32-column chunk of the S stage each
 constexpr int SW_EPI_THREADS = SW_EPI_WARPS * 32;
 constexpr int SW_THREADS = 64 + SW_EPI_THREADS;
@@ -34,8 +35,11 @@ struct SweepCfg {
   static constexpr int S_COLS = S16 ? 64 : BK;                         // feature columns per 128-byte row of an S operand
   static constexpr int G_BYTES = H16 ? Q_G_BYTES / 2 : (X3 ? 2 * Q_G_BYTES : Q_G_BYTES);   // one G buffer: 64 rows x 256 columns
   static constexpr int G_BUFS = H16 ? 2 : 1;
-  static constexpr int STAGES = X3 ? 5 : 9;
-  static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + Q_CTRL_BYTES;
+  // 3xTF32: G as hi + lo takes 128 KiB; a SIXTH ring stage fits only with the control block cut to its first 3 KiB (one
+  // (r_j, a_j) buffer instead of two, the row-sum partials on top of it: SweepCtrl)
+  static constexpr int STAGES = X3 ? 6 : 9;
+  static constexpr int CTRL_BYTES = X3 ? Q_CTRL_SHORT_BYTES : Q_CTRL_BYTES;
+  static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + CTRL_BYTES;
   static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : (X3 ? 2 * (Q_GROUP / BK) : Q_GROUP / BK);   // ring stages per column group and dZ^T tile
   static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
 };
@@ -53,14 +57,21 @@ struct SweepCtrl {
   uint64_t g_copied[2];           // quad kernel, per CTA: the other pair's CTA has copied our G tile out
   uint32_t tmem_base;
   uint32_t pad;
-  alignas(16) float col_r[2][Q_GROUP];   // r_j per S stage (read as float4)
-  alignas(16) float col_a[2][Q_GROUP];   // a_j per S stage
   float negc[MAX_KERNELS];
   float w[MAX_KERNELS];
   double red[SW_EPI_WARPS][2];
+  // (r_j, a_j) of a column group, read as float4.  Buffer 0 first: the 3xTF32 mode has room for the block only up to
+  // here (Q_CTRL_SHORT_BYTES) -- it uses buffer 0 for every group (one more barrier per group) and lays the row-sum
+  // partials of an item over it (2 x 256 floats = 8 x 64)
+  alignas(16) float col_r0[Q_GROUP];
+  alignas(16) float col_a0[Q_GROUP];
+  alignas(16) float col_r1[Q_GROUP];     // buffer 1: the S stage's other parity
+  alignas(16) float col_a1[Q_GROUP];
   float part[8][64];              // row-sum partials of an item (2 lane halves x 4 column chunks per row)
 };
 static_assert(sizeof(SweepCtrl) <= Q_CTRL_BYTES, "SweepCtrl does not fit its smem slot");
+static_assert(offsetof(SweepCtrl, col_r1) <= Q_CTRL_SHORT_BYTES && offsetof(SweepCtrl, col_a0) == offsetof(SweepCtrl, col_r0) + Q_GROUP * 4,
+              "the short control block ends behind its first column buffers");
 static_assert(SweepCfg<0>::SMEM_BYTES <= 232448 && SweepCfg<1>::SMEM_BYTES <= 232448 && SweepCfg<3>::SMEM_BYTES <= 232448,
               "smem budget");
 
@@ -438,9 +449,11 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         const uint32_t u = (uint32_t)(gc >> 1);
         const int gb = gc % GB;
         const uint32_t gu = (uint32_t)(gc / GB);
+        const int cbuf = X3 ? 0 : b;                        // (3xTF32: one column buffer, see SweepCtrl)
+        if (X3 && g > 0) named_barrier_sync(1, SW_EPI_THREADS);     // ... which every warp has finished reading
         if (et < Q_GROUP) {
-          ctl->col_r[b][et] = (float)nxt_r;
-          ctl->col_a[b][et] = nxt_a;
+          (cbuf ? ctl->col_r1 : ctl->col_r0)[et] = (float)nxt_r;
+          (cbuf ? ctl->col_a1 : ctl->col_a0)[et] = nxt_a;
           if (g + 1 < it.ng) {
             nxt_r = p.racc[(it.g_begin + g + 1) * Q_GROUP + et];
             nxt_a = p.a[(it.g_begin + g + 1) * Q_GROUP + et];
@@ -457,8 +470,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(s_empty_leader0 + 8u * (uint32_t)b);
         uint32_t gp[H16 ? 16 : 32];                            // packed binary16 pairs / TF32 words of this row's G
-        const float4 *cr4 = reinterpret_cast<const float4 *>(&ctl->col_r[b][j0]);
-        const float4 *ca4 = reinterpret_cast<const float4 *>(&ctl->col_a[b][j0]);
+        const float4 *cr4 = reinterpret_cast<const float4 *>(&(cbuf ? ctl->col_r1 : ctl->col_r0)[j0]);
+        const float4 *ca4 = reinterpret_cast<const float4 *>(&(cbuf ? ctl->col_a1 : ctl->col_a0)[j0]);
         if (FAST) {
           const float2 ri2 = make_float2(ri, ri), m2s2 = make_float2(m2s, m2s), nc2 = make_float2(negc_last, negc_last);
           const float2 half2c = make_float2(0.5f, 0.5f), rc2 = make_float2(rc, rc);
@@ -506,7 +519,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float rj = ctl->col_r[b][j0 + j], aj = ctl->col_a[b][j0 + j];
+            const float rj = (cbuf ? ctl->col_r1 : ctl->col_r0)[j0 + j], aj = (cbuf ? ctl->col_a1 : ctl->col_a0)[j0 + j];
             const float Lraw = fmaf(m2s, __uint_as_float(v[j]), ri + rj);
             const float L = fmaxf(Lraw, 0.f);
             float K, Q;
@@ -571,17 +584,22 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       // ---- end of the item: forward sums, row sums of G, write-out ----
       accM += (double)(ai_m * ((tM2.x + tM2.y) + tMs));
       accD += (double)(ai_m * ((tD2.x + tD2.y) + tDs));
-      ctl->part[jh * 4 + cq][r] = rowsum * gs_inv;
+      // (3xTF32: the partials lie over the column buffers, which the item's last group has finished with only after a
+      //  barrier -- and which the next item must not refill before they have been summed)
+      float (*part)[64] = X3 ? reinterpret_cast<float (*)[64]>(ctl->col_r0) : ctl->part;
+      if (X3) named_barrier_sync(1, SW_EPI_THREADS);
+      part[jh * 4 + cq][r] = rowsum * gs_inv;
       named_barrier_sync(1, SW_EPI_THREADS);
       if (et < 64) {
         // 8 partials per row (2 lane halves x 4 column chunks) -> rowsum(G')_i of this item's columns, for apply_grad
         float tot = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += ctl->part[k][et];
+        for (int k = 0; k < 8; ++k) tot += part[k][et];
         // (only this panel's own rows: rows past the range end may belong to another panel with another split)
         if ((int)rank * 64 + et < it.rows_here)
           p.rowsum[(size_t)(it.ypass * SW_MAX_SPLIT + it.slab) * p.n_pad + it.row_base + (int)rank * 64 + et] = tot;
       }
+      if (X3) named_barrier_sync(1, SW_EPI_THREADS);
       // U[slab][i, f] = -(G' Z)_i[f] of this item's columns (rowsum_i z_i is added by edrl_mmd_apply_grad)
       mbar_wait(&ctl->dz_full, (uint32_t)(itn & 1));
       tc_fence_after();
@@ -995,9 +1013,10 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
         const int b = sc & 1;
         const uint32_t u = (uint32_t)(sc >> 1);
         ++sc;
+        const int cbuf = b;
         if (et < Q_GROUP) {
-          ctl->col_r[b][et] = (float)nxt_r;
-          ctl->col_a[b][et] = nxt_a;
+          (cbuf ? ctl->col_r1 : ctl->col_r0)[et] = (float)nxt_r;
+          (cbuf ? ctl->col_a1 : ctl->col_a0)[et] = nxt_a;
           if (g + 2 < it.ng) {                              // this pair's next group
             nxt_r = p.racc[(it.g_begin + g + 2) * Q_GROUP + et];
             nxt_a = p.a[(it.g_begin + g + 2) * Q_GROUP + et];
@@ -1014,8 +1033,8 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(s_empty_leader0 + 8u * (uint32_t)b);
         uint32_t gp[H16 ? 16 : 32];                            // packed binary16 pairs / TF32 words of this row's G
-        const float4 *cr4 = reinterpret_cast<const float4 *>(&ctl->col_r[b][j0]);
-        const float4 *ca4 = reinterpret_cast<const float4 *>(&ctl->col_a[b][j0]);
+        const float4 *cr4 = reinterpret_cast<const float4 *>(&(cbuf ? ctl->col_r1 : ctl->col_r0)[j0]);
+        const float4 *ca4 = reinterpret_cast<const float4 *>(&(cbuf ? ctl->col_a1 : ctl->col_a0)[j0]);
         if (FAST) {
           const float2 ri2 = make_float2(ri, ri), m2s2 = make_float2(m2s, m2s), nc2 = make_float2(negc_last, negc_last);
           const float2 half2c = make_float2(0.5f, 0.5f), rc2 = make_float2(rc, rc);
@@ -1059,7 +1078,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float rj = ctl->col_r[b][j0 + j], aj = ctl->col_a[b][j0 + j];
+            const float rj = (cbuf ? ctl->col_r1 : ctl->col_r0)[j0 + j], aj = (cbuf ? ctl->col_a1 : ctl->col_a0)[j0 + j];
             const float Lraw = fmaf(m2s, __uint_as_float(v[j]), ri + rj);
             const float L = fmaxf(Lraw, 0.f);
             float K, Q;
