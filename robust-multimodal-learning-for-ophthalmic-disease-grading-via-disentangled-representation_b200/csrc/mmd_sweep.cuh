@@ -37,8 +37,12 @@ struct SweepCfg {
   static constexpr int G_BUFS = H16 ? 2 : 1;
   // 3xTF32: G as hi + lo takes 128 KiB; a SIXTH ring stage fits only with the control block cut to its first 3 KiB (one
   // (r_j, a_j) buffer instead of two, the row-sum partials on top of it: SweepCtrl)
+  // (TF32 with the short block and a TENTH stage -- 64 KiB of G + 160 KiB + 3 KiB = 232448 B as well -- measured no
+  //  faster: 0.854 against 0.850 ms at N=8192, d=512, 1.86 against 1.88 ms at d=1024: that mode is bound by throughput,
+  //  and the extra barriers cost what the stage buys)
+  static constexpr bool SHORT_CTRL = X3;
   static constexpr int STAGES = X3 ? 6 : 9;
-  static constexpr int CTRL_BYTES = X3 ? Q_CTRL_SHORT_BYTES : Q_CTRL_BYTES;
+  static constexpr int CTRL_BYTES = SHORT_CTRL ? Q_CTRL_SHORT_BYTES : Q_CTRL_BYTES;
   static constexpr int SMEM_BYTES = G_BUFS * G_BYTES + STAGES * P2_STAGE + CTRL_BYTES;
   static constexpr int P_ATOMS = H16 ? Q_GROUP / 64 : (X3 ? 2 * (Q_GROUP / BK) : Q_GROUP / BK);   // ring stages per column group and dZ^T tile
   static constexpr int P_ATOM_COLS = H16 ? 64 : BK;
@@ -449,8 +453,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         const uint32_t u = (uint32_t)(gc >> 1);
         const int gb = gc % GB;
         const uint32_t gu = (uint32_t)(gc / GB);
-        const int cbuf = X3 ? 0 : b;                        // (3xTF32: one column buffer, see SweepCtrl)
-        if (X3 && g > 0) named_barrier_sync(1, SW_EPI_THREADS);     // ... which every warp has finished reading
+        const int cbuf = Cfg::SHORT_CTRL ? 0 : b;           // (short control block: one column buffer, see SweepCtrl)
+        if (Cfg::SHORT_CTRL && g > 0) named_barrier_sync(1, SW_EPI_THREADS);   // ... which every warp has finished reading
         if (et < Q_GROUP) {
           (cbuf ? ctl->col_r1 : ctl->col_r0)[et] = (float)nxt_r;
           (cbuf ? ctl->col_a1 : ctl->col_a0)[et] = nxt_a;
@@ -586,8 +590,8 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
       accD += (double)(ai_m * ((tD2.x + tD2.y) + tDs));
       // (3xTF32: the partials lie over the column buffers, which the item's last group has finished with only after a
       //  barrier -- and which the next item must not refill before they have been summed)
-      float (*part)[64] = X3 ? reinterpret_cast<float (*)[64]>(ctl->col_r0) : ctl->part;
-      if (X3) named_barrier_sync(1, SW_EPI_THREADS);
+      float (*part)[64] = Cfg::SHORT_CTRL ? reinterpret_cast<float (*)[64]>(ctl->col_r0) : ctl->part;
+      if (Cfg::SHORT_CTRL) named_barrier_sync(1, SW_EPI_THREADS);
       part[jh * 4 + cq][r] = rowsum * gs_inv;
       named_barrier_sync(1, SW_EPI_THREADS);
       if (et < 64) {
@@ -599,7 +603,7 @@ mmd_sweep256_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_con
         if ((int)rank * 64 + et < it.rows_here)
           p.rowsum[(size_t)(it.ypass * SW_MAX_SPLIT + it.slab) * p.n_pad + it.row_base + (int)rank * 64 + et] = tot;
       }
-      if (X3) named_barrier_sync(1, SW_EPI_THREADS);
+      if (Cfg::SHORT_CTRL) named_barrier_sync(1, SW_EPI_THREADS);
       // U[slab][i, f] = -(G' Z)_i[f] of this item's columns (rowsum_i z_i is added by edrl_mmd_apply_grad)
       mbar_wait(&ctl->dz_full, (uint32_t)(itn & 1));
       tc_fence_after();
@@ -984,6 +988,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
         nxt_a = p.a[(it.g_begin + pairidx) * Q_GROUP + et];
       }
 
+      bool own_seen = false;                                // (short control block: one column buffer per CTA)
       for (int g = 0; g < it.ng; ++g, ++gc) {
         const int gb = gc % GB;
         const uint32_t gu = (uint32_t)(gc / GB);
@@ -1013,7 +1018,9 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
         const int b = sc & 1;
         const uint32_t u = (uint32_t)(sc >> 1);
         ++sc;
-        const int cbuf = b;
+        const int cbuf = Cfg::SHORT_CTRL ? 0 : b;
+        if (Cfg::SHORT_CTRL && own_seen) named_barrier_sync(1, SW_EPI_THREADS);   // (every warp has finished reading the buffer)
+        own_seen = true;
         if (et < Q_GROUP) {
           (cbuf ? ctl->col_r1 : ctl->col_r0)[et] = (float)nxt_r;
           (cbuf ? ctl->col_a1 : ctl->col_a0)[et] = nxt_a;
@@ -1131,13 +1138,15 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
       // ---- end of the item: forward sums, row sums of G, write-out ----
       accM += (double)(ai_m * ((tM2.x + tM2.y) + tMs));
       accD += (double)(ai_m * ((tD2.x + tD2.y) + tDs));
-      ctl->part[jh * 4 + cq][r] = rowsum * gs_inv;
+      float (*part)[64] = Cfg::SHORT_CTRL ? reinterpret_cast<float (*)[64]>(ctl->col_r0) : ctl->part;
+      if (Cfg::SHORT_CTRL) named_barrier_sync(1, SW_EPI_THREADS);
+      part[jh * 4 + cq][r] = rowsum * gs_inv;
       named_barrier_sync(1, SW_EPI_THREADS);
       if (et < 64) {
         // 8 partials per row (2 lane halves x 4 column chunks) -> rowsum(G')_i of this item's columns, for apply_grad
         float tot = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += ctl->part[k][et];
+        for (int k = 0; k < 8; ++k) tot += part[k][et];
         // (only this panel's own rows: rows past the range end may belong to another panel with another split)
         // (each pair saw half of the column groups: the two partial sums are added in the slot zeroed by prep; two
         //  addends commute, so the result does not depend on the order)
@@ -1145,6 +1154,7 @@ mmd_sweep_quad_kernel(const __grid_constant__ CUtensorMap tm_z64, const __grid_c
           atomicAdd(&p.rowsum[(size_t)(it.ypass * SW_MAX_SPLIT + it.slab) * p.n_pad + it.row_base + (int)rank * 64 + et],
                     tot);
       }
+      if (Cfg::SHORT_CTRL) named_barrier_sync(1, SW_EPI_THREADS);
       // U[slab][i, f] = -(G' Z)_i[f] of this item's columns (rowsum_i z_i is added by edrl_mmd_apply_grad)
       mbar_wait(&ctl->dz_full, (uint32_t)(itn & 1));
       tc_fence_after();
