@@ -3,9 +3,13 @@
 #pragma once
 
 // ----------------------------------------------------------------------------- K3q: CTA-pair sweep, 256-column S tiles
-// Same decomposition as mmd_bwd_pair_kernel (S phase -> G -> transposed P phase over a 2-CTA cluster), but the S
-// phase works on TWO column tiles at once: tcgen05 M = 128 (64 rows of the panel per CTA), N = 256 (128 rows of Z_J
-// per CTA).  With 64 A rows per CTA the N = 128 S phase re-read 4 KiB of shared memory per 32-clk MMA (the whole
+// One 2-CTA cluster (an SM pair, tcgen05 cta_group::2) owns a 128-row panel I of Z and 512 feature columns:
+//   S phase   S_IJ = Z_I Z_J^T                 M = 128 (64 rows of the panel per CTA), N = 256 (128 rows of Z_J per CTA), K = d
+//   epilogue  each CTA turns its 64 x 256 slice of S into G in its own shared memory
+//   P phase   dZ^T[f, i] += Zt[f, j] G[i, j]   M = 256 features (128 per CTA), N = 128 rows i (the two CTAs' G halves are the
+//             two halves of the B operand -- no exchange), K = 256 columns j
+// The S phase works on TWO 128-column tiles at once: with 64 A rows per CTA an N = 128 S phase (the first version of this
+// decomposition, the deleted separate backward kernel) re-read 4 KiB of shared memory per 32-clk MMA (the whole
 // 128 B/clk port); N = 256 reads 6 KiB per 64 clk, the Z_I chunk is fetched once per 256 columns instead of per 128,
 // and the MMAs are twice as long (half the issue slots).  Z_I is streamed (two 32-column chunks per ring stage), the
 // ring has 9 stages of 16 KiB, G is 64 rows x 256 columns (64 KiB) per CTA.

@@ -445,7 +445,7 @@ def test_work_list_shapes_fused_vs_separate_kernels(raw, ns, nt, d, prec, flag):
 @pytest.mark.parametrize("ns,nt,d", [(700, 650, 1100), (900, 1100, 400)])
 def test_generic_bandwidths_in_the_sweeps(raw, ns, nt, d, prec, flag):
     """kernel_mul != 2 / kernel_num != 5 take the generic exponential path of the epilogue: the quad sweep (d = 1100) and
-    the pair sweep (d = 400) against the separate kernels and the fp64 oracle."""
+    the pair sweep (d = 400) against the separate forward + backward entry points and the fp64 oracle."""
     from gpu_util import raw_apply_grad, raw_forward_grad
     rng = np.random.default_rng(ns + d)
     x = rng.standard_normal((ns, d)).astype(np.float32)
